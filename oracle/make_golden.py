@@ -1,0 +1,265 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference.
+
+Run in the build container only (needs /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden [--only NAME]
+
+The reference ships no golden vectors; these files pin both the
+oracle (tests/test_oracle_golden.py) and the CUDA path (tests/test_gpu_parity.py)
+to what the reference's own code returns:
+  src/third_party/aniposelib/cameras.py  Camera/FisheyeCamera/CameraGroup
+  src/pipeline/step2_crossviewmatching.py  geometry_affinity2, matchSVT
+  src/utils/multicam_toolbox.py  triangulatePoints
+Each .npz stores the rig (camera dict fields as arrays), the inputs and every
+output, so that nothing under /root/reference is needed at test time.
+"""
+import argparse
+import os
+import sys
+import time
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from macaque_3d_pose_estimation_b200 import synth  # noqa: E402
+
+
+def _import_reference():
+    sys.dont_write_bytecode = True
+    for name in ("h5py", "imgstore", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    from src.third_party.aniposelib import cameras as ref_cameras
+    # numba JIT warm-up so that ref_seconds excludes compilation
+    cg = ref_cameras.CameraGroup.from_dicts(synth.make_rig(3, "pinhole", seed=1))
+    X = synth.make_tracks(1, 1, seed=1).reshape(-1, 3)
+    p2 = cg.project(X)
+    cg.reprojection_error(cg.triangulate(p2), p2, mean=True)
+    cg.triangulate_ransac(p2[:, :2])
+    return ref_cameras
+
+
+def rig_arrays(cams):
+    """Flatten camera dicts into arrays that np.savez can hold."""
+    C = len(cams)
+    model = np.zeros(C, dtype=np.int32)
+    K = np.zeros((C, 3, 3))
+    dist = np.zeros((C, 14))
+    ndist = np.zeros(C, dtype=np.int32)
+    rvec = np.zeros((C, 3))
+    tvec = np.zeros((C, 3))
+    xi = np.zeros(C)
+    for i, d in enumerate(cams):
+        if d.get("fisheye"):
+            model[i] = 1
+        elif d.get("omnidir"):
+            model[i] = 2
+        K[i] = np.array(d["K"] if model[i] == 2 else d["matrix"])
+        dd = np.array(d["D"] if model[i] == 2 else d["distortions"], dtype=np.float64).ravel()
+        dist[i, :dd.size] = dd
+        ndist[i] = dd.size
+        rvec[i] = d["rotation"]
+        tvec[i] = d["translation"]
+        xi[i] = d.get("xi", [0.0])[0]
+    return dict(rig_model=model, rig_K=K, rig_dist=dist, rig_ndist=ndist,
+                rig_rvec=rvec, rig_tvec=tvec, rig_xi=xi,
+                rig_names=np.array([d["name"] for d in cams]))
+
+
+def observations(cg, n_frames, n_animals, seed, **corrupt_kw):
+    X = synth.make_tracks(n_frames, n_animals, seed=seed).reshape(-1, 3)
+    clean = cg.project(X)
+    return X, synth.corrupt(clean, seed=seed, **corrupt_kw)
+
+
+def case_dlt(ref, name, n_cams, model, n_frames, n_animals, seed, **kw):
+    cams = synth.make_rig(n_cams, model, seed=seed)
+    cg = ref.CameraGroup.from_dicts(cams)
+    X, p2d = observations(cg, n_frames, n_animals, seed, **kw)
+    und = np.stack([cam.undistort_points(np.copy(p2d[c])) for c, cam in enumerate(cg.cameras)])
+    t0 = time.time()
+    p3d = cg.triangulate(p2d)
+    t_tri = time.time() - t0
+    p3d_noundist = cg.triangulate(und, undistort=False)
+    err_full = cg.reprojection_error(p3d, p2d, mean=False)
+    t0 = time.time()
+    err_mean = cg.reprojection_error(p3d, p2d, mean=True)
+    t_err = time.time() - t0
+    proj = cg.project(X)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rig_arrays(cams), X_true=X, p2d=p2d,
+                        undistorted=und, p3d=p3d, p3d_noundist=p3d_noundist, err_full=err_full,
+                        err_mean=err_mean, proj_true=proj,
+                        ref_seconds=np.array([t_tri, t_err]))
+    print(name, "N=%d tri %.2fs err %.2fs" % (p2d.shape[1], t_tri, t_err), flush=True)
+
+
+def case_ransac(ref, name, n_cams, model, n_frames, n_animals, seed, min_cams=2, extra=None, **kw):
+    cams = synth.make_rig(n_cams, model, seed=seed)
+    cg = ref.CameraGroup.from_dicts(cams)
+    X, p2d = observations(cg, n_frames, n_animals, seed, **kw)
+    if extra is not None:
+        p2d = extra(p2d, cg, X)
+    # instrument: count subset evaluations per call
+    calls = {"n": 0}
+    orig = ref.CameraGroup.triangulate
+
+    def counting(self, *a, **k):
+        calls["n"] += 1
+        return orig(self, *a, **k)
+    ref.CameraGroup.triangulate = counting
+    try:
+        t0 = time.time()
+        out, picked, pts2d, errs = cg.triangulate_ransac(np.copy(p2d), min_cams=min_cams)
+        dt = time.time() - t0
+    finally:
+        ref.CameraGroup.triangulate = orig
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rig_arrays(cams), X_true=X, p2d=p2d,
+                        min_cams=np.array(min_cams), p3d=out, picked=picked, points_2d=pts2d,
+                        errors=errs, n_subsets_evaluated=np.array(calls["n"]),
+                        ref_seconds=np.array([dt]))
+    print(name, "N=%d ransac %.1fs  %.1f subsets/pt" % (p2d.shape[1], dt, calls["n"] / p2d.shape[1]),
+          flush=True)
+
+
+def edge_points(p2d, cg, X):
+    """Hand-made edge cases of SURVEY.md §8c written over the first points."""
+    p = p2d
+    C = p.shape[0]
+    rng = np.random.default_rng(7)
+    p[:, 0] = np.nan                                  # all-NaN point
+    p[:, 1] = np.nan
+    p[2, 1] = cg.cameras[2].project(X[1]).ravel()     # exactly one valid view
+    p[:, 2] = np.nan                                  # two valid views (min_cams=3 run too)
+    p[[1, 4], 2] = cg.project(X[2:3])[[1, 4], 0]
+    p[3, 3, 1] = np.nan                               # NaN only in y of one view
+    p[:, 4] = rng.uniform([0, 0], [2048, 1536], size=(C, 2))   # all-garbage point
+    p[:, 5] = cg.project(X[5:6])[:, 0]                # single gross outlier at camera 0
+    p[0, 5] += np.array([80.0, -45.0])
+    p[:, 6] = cg.project(X[6:7])[:, 0]                # exact, noise-free point
+    p[:, 7] = cg.project(X[7:8])[:, 0]                # outlier at the last camera
+    p[C - 1, 7] += np.array([-60.0, 30.0])
+    p[:, 8] = np.nan                                  # two views, one of them with y = NaN
+    p[[0, 5], 8] = cg.project(X[8:9])[[0, 5], 0]
+    p[5, 8, 1] = np.nan
+    p[:, 9] = cg.project(X[9:10])[:, 0]               # x = NaN but y finite (view dropped)
+    p[2, 9, 0] = np.nan
+    return p
+
+
+def case_crossview(ref, name, n_frames, seed, drop=0.0):
+    from src.pipeline import step2_crossviewmatching as s2
+    from src.utils import multicam_toolbox as mct
+    import cv2
+    C, A, J = 8, 6, 17
+    cams = synth.make_rig(C, "pinhole", seed=seed)
+    rng = np.random.default_rng(seed + 5)
+    camparam = {"camera_id": [d["name"] for d in cams], "K": [], "xi": [], "D": [],
+                "rvecs": [], "tvecs": [], "pmat": []}
+    for d in cams:
+        R, _ = cv2.Rodrigues(np.array(d["rotation"]))
+        t = np.array(d["translation"]).reshape(3, 1)
+        camparam["K"].append(np.array(d["matrix"]))
+        camparam["xi"].append(np.zeros((1, 1)))
+        camparam["D"].append(np.zeros((1, 4)))
+        camparam["rvecs"].append(np.array(d["rotation"]).reshape(3, 1))
+        camparam["tvecs"].append(t)
+        camparam["pmat"].append(np.hstack([R, t]))
+    X = synth.make_tracks(n_frames, A, seed=seed)               # (F, A, J, 3)
+    frames = []
+    for f in range(n_frames):
+        kps, dim, owner = [], [0], []
+        for c in range(C):
+            P = camparam["pmat"][c]
+            for a in range(A):
+                if rng.random() < drop:
+                    continue
+                Xc = X[f, a] @ P[:, :3].T + P[:, 3]
+                xy = Xc[:, :2] / Xc[:, 2:3] + rng.normal(0, 4e-4, size=(J, 2))
+                sc = rng.uniform(0.3, 1.0, size=J)
+                sc[rng.random(J) < 0.1] = 0.0
+                kps.append(np.concatenate([xy, sc[:, None]], axis=1))
+                owner.append(a)
+            dim.append(len(kps))
+        kp = np.array(kps)
+        dimGroup = np.array(dim)
+        t0 = time.time()
+        aff = s2.geometry_affinity2(kp.copy(), dimGroup, "", camparam=camparam)
+        t_aff = time.time() - t0
+        W = 0.8 * aff
+        W *= (aff > 0)
+        W = np.nan_to_num(W)
+        t0 = time.time()
+        match = s2.matchSVT(W.copy(), dimGroup, alpha=0.5, _lambda=50, dual_stochastic_SVT=False)
+        t_svt = time.time() - t0
+        # mct.triangulatePoints on animal 0 of this frame (views that saw it)
+        M = kp.shape[0]
+        kp2d = np.full((C, J, 3), np.nan)
+        kp2d[:, :, 2] = 0.0
+        for i in range(M):
+            c = int(np.searchsorted(dimGroup, i, side="right") - 1)
+            if owner[i] == 0:
+                kp2d[c] = kp[i]
+        frame_use = (~np.isnan(kp2d[:, :, 0]) & (kp2d[:, :, 2] >= 0.1)).T
+        und = [np.nan_to_num(kp2d[c, :, :2]) for c in range(C)]
+        p3d_ls = mct.triangulatePoints("", und, frame_use, True, camparam=camparam)
+        frames.append(dict(kp=kp, dimGroup=dimGroup, owner=np.array(owner), aff=aff, W=W,
+                           match=match, ls_xy=np.array(und), ls_use=frame_use, ls_p3d=p3d_ls,
+                           t=np.array([t_aff, t_svt])))
+        print(name, "frame", f, "M=%d aff %.2fs svt %.2fs" % (M, t_aff, t_svt), flush=True)
+    arrs = rig_arrays(cams)
+    for f, fr in enumerate(frames):
+        for k, v in fr.items():
+            arrs["f%d_%s" % (f, k)] = v
+    arrs["n_frames"] = np.array(n_frames)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    ref = _import_reference()
+    S = 20261018
+    cases = {
+        "dlt_pinhole_c8": lambda: case_dlt(ref, "dlt_pinhole_c8", 8, "pinhole", 60, 2, S + 1, p_missing=0.1),
+        "dlt_pinhole8_c8": lambda: case_dlt(ref, "dlt_pinhole8_c8", 8, "pinhole8", 20, 2, S + 2, p_missing=0.1),
+        "dlt_fisheye_c8": lambda: case_dlt(ref, "dlt_fisheye_c8", 8, "fisheye", 30, 2, S + 3, p_missing=0.1),
+        "dlt_pinhole_c2": lambda: case_dlt(ref, "dlt_pinhole_c2", 2, "pinhole", 15, 2, S + 4, p_missing=0.05),
+        "dlt_pinhole_c3": lambda: case_dlt(ref, "dlt_pinhole_c3", 3, "pinhole", 15, 2, S + 5, p_missing=0.1),
+        "dlt_pinhole_c16": lambda: case_dlt(ref, "dlt_pinhole_c16", 16, "pinhole", 15, 2, S + 6, p_missing=0.1),
+        "ransac_pinhole_c8": lambda: case_ransac(ref, "ransac_pinhole_c8", 8, "pinhole", 40, 2, S + 11,
+                                                  p_outlier=0.2, p_missing=0.1),
+        "ransac_pinhole_c8_min3": lambda: case_ransac(ref, "ransac_pinhole_c8_min3", 8, "pinhole", 12, 2, S + 12,
+                                                       min_cams=3, p_outlier=0.2, p_missing=0.1),
+        "ransac_fisheye_c8": lambda: case_ransac(ref, "ransac_fisheye_c8", 8, "fisheye", 10, 2, S + 13,
+                                                  p_outlier=0.2, p_missing=0.1),
+        "ransac_pinhole_c3": lambda: case_ransac(ref, "ransac_pinhole_c3", 3, "pinhole", 12, 2, S + 14,
+                                                  p_outlier=0.2, p_missing=0.1),
+        "ransac_pinhole_c12": lambda: case_ransac(ref, "ransac_pinhole_c12", 12, "pinhole", 1, 2, S + 15,
+                                                   p_outlier=0.08, p_missing=0.1),
+        "ransac_edges_c8": lambda: case_ransac(ref, "ransac_edges_c8", 8, "pinhole", 1, 1, S + 16,
+                                                extra=edge_points),
+        "ransac_edges_c8_min3": lambda: case_ransac(ref, "ransac_edges_c8_min3", 8, "pinhole", 1, 1, S + 16,
+                                                     min_cams=3, extra=edge_points),
+        "ransac_noisy_c8": lambda: case_ransac(ref, "ransac_noisy_c8", 8, "pinhole", 6, 2, S + 17,
+                                                noise=0.55, p_outlier=0.1, p_missing=0.1),
+        "crossview_m48": lambda: case_crossview(ref, "crossview_m48", 4, S + 21),
+        "crossview_ragged": lambda: case_crossview(ref, "crossview_ragged", 3, S + 22, drop=0.15),
+    }
+    for name, fn in cases.items():
+        if args.only and args.only != name:
+            continue
+        fn()
+
+
+if __name__ == "__main__":
+    main()
