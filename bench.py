@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 multi-view 3D reconstruction hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload dlt|ransac] [--impl reference]
+
+metric  : triangulated joint-instances/sec (BASELINE.json)
+workload: "dlt"    = BASELINE config 2: 8-view undistort + DLT triangulate + mean reprojection
+                     error, 4 macaques x 17 joints x 1M frames = 6.8e7 joint-instances per GPU
+          "ransac" = BASELINE config 3: 8-view triangulate_ransac (all subsets, min 2 views),
+                     20 % outlier detections, frame-sharded
+A step is one pass of the hot path over the whole resident batch.  Inputs (8.7 GB for
+"dlt") are far larger than the 126 MB L2, so no flush is needed between iterations.
+N > 1: one process per GPU (torchrun), weak scaling (each rank owns its own frame chunk of
+the same size), no data-path collective; the NCCL gather of the 3D results to rank 0 is
+timed separately ("gather").
+
+`--impl reference` times the CPU port of the reference's NumPy/OpenCV path (oracle/) on
+the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0
+BYTES_PER_INSTANCE = {"dlt": lambda C: 16 * C + 32, "ransac": lambda C: 33 * C + 32}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic workload, generated on the device
+# ------------------------------------------------------------------------------------------
+
+def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    root0 = torch.rand((n_animals, 3), generator=g, device=device, dtype=f64)
+    lo = torch.tensor([-900.0, -900.0, 0.0], device=device, dtype=f64)
+    hi = torch.tensor([900.0, 900.0, 1500.0], device=device, dtype=f64)
+    root0 = lo + root0 * (hi - lo)
+    steps = torch.randn((n_frames, n_animals, 3), generator=g, device=device, dtype=f64) * 15.0
+    root = root0[None] + torch.cumsum(steps, dim=0)
+    del steps
+    # keep the animals in the cage: reflect the walk into the box
+    span = hi - lo + 200.0
+    root = lo - 100.0 + (span - ((root - lo + 100.0) % (2 * span) - span).abs()).abs()
+    skel = torch.randn((n_animals, n_joints, 3), generator=g, device=device, dtype=f64) * 120.0
+    X = (root[:, :, None, :] + skel[None]).reshape(-1, 3).contiguous()
+    del root
+    xy = cg.project(X)                                         # our own projection kernel
+    C, N = xy.shape[0], xy.shape[1]
+    for c in range(C):                                         # plane by plane: bounded temporaries
+        xy[c] += torch.randn((N, 2), generator=g, device=device, dtype=f64) * 0.3
+        if workload == "ransac":
+            o = torch.rand((N,), generator=g, device=device) < 0.2
+            xy[c] += o[:, None] * torch.randn((N, 2), generator=g, device=device, dtype=f64) * 60.0
+        m = torch.rand((N,), generator=g, device=device) < 0.1
+        xy[c][m] = float("nan")
+    return X, xy
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's NumPy/OpenCV path)
+# ------------------------------------------------------------------------------------------
+
+def _cpu_chunk(args):
+    dicts, p2d, workload = args
+    import numpy as np
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    cams = fixtures.cams_from_dicts(dicts)
+    if workload == "dlt":
+        p3d = og.triangulate_loops(cams, p2d)
+        og.reprojection_error_loops(cams, p3d, p2d, mean=True)
+    else:
+        og.triangulate_ransac_loops(cams, p2d, min_cams=2)
+    return p2d.shape[1]
+
+
+def cpu_workload(workload, n_points, seed):
+    import numpy as np
+    from macaque_3d_pose_estimation_b200 import synth
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    n_frames = max(1, n_points // (2 * 17))
+    X = synth.make_tracks(n_frames, 2, seed=seed).reshape(-1, 3)[:n_points]
+    p2d = synth.corrupt(og.project(cams, X), seed=seed, p_outlier=0.2 if workload == "ransac" else 0.0,
+                        p_missing=0.1)
+    return dicts, p2d
+
+
+def time_cpu(workload, n_points, procs, seed=20261018):
+    """joint-instances/s of the loop-faithful port on `procs` host processes."""
+    import numpy as np
+    dicts, p2d = cpu_workload(workload, n_points, seed)
+    n = p2d.shape[1]
+    if procs <= 1:
+        _cpu_chunk((dicts, p2d[:, :8], workload))              # warm caches / imports
+        t0 = time.perf_counter()
+        _cpu_chunk((dicts, p2d, workload))
+        return n / (time.perf_counter() - t0), n
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    chunks = np.array_split(np.arange(n), procs)
+    jobs = [(dicts, np.ascontiguousarray(p2d[:, c]), workload) for c in chunks if c.size]
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_chunk, [(dicts, p2d[:, :8].copy(), workload)] * procs)   # spawn + import warm-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, jobs)
+        dt = time.perf_counter() - t0
+    return n / dt, n
+
+
+def run_reference(args):
+    """--impl reference: the CPU port on all host cores, same metric / config keys."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    sample = 2 * 17 * (1000 if args.workload == "dlt" else 6) * max(1, procs // 2)
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.steps):
+        v, n = time_cpu(args.workload, sample, procs)
+        vals.append(v)
+        if time.perf_counter() - t_all > 240:
+            break
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "triangulated joint-instances/sec", "value": value,
+        "unit": "joint-instances/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, 8, n),
+        "cpu_baseline": {"value": value, "unit": "joint-instances/s", "cores": procs, "kind": "port",
+                         "sample": "%d joint-instances per step (cfg-1 rig: 8 pinhole cameras, 2 animals x 17 "
+                                   "joints), loop-faithful NumPy/OpenCV port of the reference in oracle/, "
+                                   "%d spawn processes" % (n, procs)},
+        "e2e": {"value": value, "unit": "joint-instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, C, n_per_gpu):
+    names = {"dlt": "cfg2: 8-view undistort + DLT triangulate + mean reprojection_error, 4 macaques x 17 joints",
+             "ransac": "cfg3: 8-view triangulate_ransac (all camera subsets, min_cams=2), 20% outlier detections"}
+    return {"workload": names[args.workload], "cameras": C, "camera_model": "pinhole(5 coeff)",
+            "joint_instances_per_gpu": int(n_per_gpu), "frames_per_gpu": int(args.frames),
+            "animals": 4, "joints": 17, "missing_views": 0.1,
+            "outliers": 0.2 if args.workload == "ransac" else 0.0,
+            "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": "frame-sharded dp%d" % args.gpus}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from macaque_3d_pose_estimation_b200 import _lib, synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.require_gpu()
+
+    C, A, J = 8, 4, 17
+    F = args.frames
+    seed = 20261018 + 2 + rank
+    cg = CameraGroup.from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2), device=local)
+    X, xy = make_device_workload(cg, F, A, J, seed, args.workload, device)
+    del X
+    N = xy.shape[1]
+    p3d = torch.empty((N, 3), dtype=torch.float64, device=device)
+    err = torch.empty((N,), dtype=torch.float64, device=device)
+    picked = torch.empty((C, N), dtype=torch.uint8, device=device) if args.workload == "ransac" else None
+    xyp = torch.empty((C, N, 2), dtype=torch.float64, device=device) if args.workload == "ransac" else None
+    nev = torch.empty((N,), dtype=torch.int32, device=device) if args.workload == "ransac" else None
+    rig = cg._rig(local)
+    stream = torch.cuda.current_stream(device)
+    sp = lambda t: None if t is None else t.data_ptr()
+
+    def step():
+        if args.workload == "dlt":
+            rc = lib.m3d_triangulate_error(rig.handle, xy.data_ptr(), N, 1, p3d.data_ptr(), err.data_ptr(),
+                                           stream.cuda_stream)
+        else:
+            rc = lib.m3d_triangulate_ransac(rig.handle, xy.data_ptr(), N, 1, 2, 0.5, 200.0, p3d.data_ptr(),
+                                            sp(picked), sp(xyp), err.data_ptr(), None, sp(nev),
+                                            stream.cuda_stream)
+        _lib.check(rc, "bench step")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = lib.m3d_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.m3d_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    # gather of the 3D results to rank 0 (the only collective of the path), timed separately
+    gather_ms = None
+    if world > 1:
+        from macaque_3d_pose_estimation_b200 import sharding
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        out = sharding.gather_results([p3d, err], F, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+        del out
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_peaks()
+    bpi = BYTES_PER_INSTANCE[args.workload](C)
+    achieved = bpi * N / (ms_per_step * 1e-3) / 1e9            # per-GPU kernel, GB/s
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
+                "kernel": "k_triangulate<undistort,err>" if args.workload == "dlt" else "k_ransac",
+                "algorithmic_bytes_per_instance": bpi,
+                "note": "path is fp64-ALU bound at reference precision (SURVEY 7); see fp64"}
+    tf = ctypes_double()
+    if lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
+        roofline["fp64_peak_tflops_measured"] = tf.value
+    extra = {}
+    if args.workload == "ransac":
+        extra["mean_subsets_per_point"] = float(nev.double().mean().item())
+        extra["selected_fraction"] = float((~torch.isnan(p3d[:, 0])).double().mean().item())
+
+    # ---- e2e: host buffers through the C-ABI host pipeline (H2D + kernel + D2H per step) ----
+    n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else N
+    e2e = None
+    try:
+        h_xy = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True)
+        h_xy.copy_(xy[:, :n_e2e])
+        h_p3d = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
+        h_err = torch.empty((n_e2e,), dtype=torch.float64, pin_memory=True)
+        h_pick = torch.empty((C, n_e2e), dtype=torch.uint8, pin_memory=True) if args.workload == "ransac" else None
+        h_xyp = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True) if args.workload == "ransac" else None
+
+        def e2e_step():
+            if args.workload == "dlt":
+                rc = lib.m3d_triangulate_error_host(rig.handle, h_xy.data_ptr(), n_e2e, 1, h_p3d.data_ptr(),
+                                                    h_err.data_ptr())
+            else:
+                rc = lib.m3d_triangulate_ransac_host(rig.handle, h_xy.data_ptr(), n_e2e, 1, 2, 0.5, 200.0,
+                                                     h_p3d.data_ptr(), sp(h_pick), sp(h_xyp), h_err.data_ptr(),
+                                                     None, None)
+            _lib.check(rc, "e2e step")
+        e2e_step()
+        torch.cuda.synchronize()
+        ke = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / ke
+        # the pipeline's output equals the resident run
+        assert torch.equal(h_p3d.nan_to_num(), p3d[:n_e2e].cpu().nan_to_num())
+        d2h = n_e2e * 32 + (n_e2e * C * 17 if args.workload == "ransac" else 0)
+        e2e = {"value": n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 16,
+               "d2h_bytes_per_step": d2h, "joint_instances": n_e2e, "ms_per_step": dt * 1e3,
+               "api": "m3d_triangulate_%s_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"
+                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": 1}
+        del h_xy, h_p3d, h_err
+    except Exception as ex:  # pragma: no cover
+        e2e = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:200]}
+
+    # ---- CPU baseline: loop-faithful port, one core, bounded sample ---------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        n_cpu = 34000 if args.workload == "dlt" else 340
+        v, n = time_cpu(args.workload, n_cpu, 1)
+        cpu = {"value": v, "unit": "joint-instances/s", "cores": 1, "kind": "port",
+               "sample": "%d joint-instances of the cfg-1 rig (8 pinhole cameras), loop-faithful NumPy/OpenCV "
+                         "port of the reference (oracle/cameragroup.py *_loops)" % n}
+
+    line = {
+        "metric": "triangulated joint-instances/sec", "value": value, "unit": "joint-instances/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, C, N), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if gather_ms is not None:
+        line["gather"] = {"ms": gather_ms, "bytes_to_rank0": int((world - 1) * N * 32),
+                          "what": "torch.distributed.gather (NCCL) of p3d+err to rank 0"}
+    line.update(extra)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctypes_double():
+    import ctypes
+    return ctypes.c_double(0.0)
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=["dlt", "ransac"], default="dlt")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6 dlt, 2e5 ransac)")
+    ap.add_argument("--e2e-points", type=int, default=0, help="joint-instances of the e2e run (0 = all)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.frames <= 0:
+        args.frames = 1000000 if args.workload == "dlt" else 200000
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+/*
+ * m3d.h — C ABI of libm3d.so: the B200 (sm_100a) multi-view 3D reconstruction hot path.
+ *
+ * The reference (sidd-bme/macaque-3d-pose-estimation) has no FFI / plugin registry: its
+ * boundary for this path is the Python object API of
+ *   src/third_party/aniposelib/cameras.py   (Camera*, CameraGroup)
+ *   src/pipeline/step2_crossviewmatching.py (geometry_affinity2, matchSVT, calc_3dpose)
+ *   src/utils/multicam_toolbox.py           (undistortPoints, triangulatePoints)
+ * Each entry point below names the reference function it replaces (file:line).  The
+ * Python host layer (macaque_3d_pose_estimation_b200/) binds these with ctypes and keeps
+ * the reference's signatures; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - every array is C-contiguous float64 unless stated, missing observation = NaN
+ *     (validity is decided on the x coordinate only, cameras.py:630,659);
+ *   - "dev" pointers are device pointers on the rig's GPU, owned by the caller;
+ *     `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous on that stream;
+ *   - "*_host" entry points take HOST pointers, run a chunked, double-buffered
+ *     H2D -> kernel -> D2H pipeline and return when the outputs are in host memory;
+ *   - return value: 0 = ok, negative = error (m3d_last_error() gives the message of the
+ *     last failure on the calling thread);
+ *   - a rig handle is immutable after creation and may be used from several threads and
+ *     streams at once.  No global state.
+ */
+#ifndef M3D_H_
+#define M3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3D_MAX_CAMS 16
+#define M3D_MAX_JOINTS 32   /* keypoints per detection in m3d_ray_affinity */
+#define M3D_MAX_DETS 128    /* detections per frame in m3d_ray_affinity / m3d_match_svt */
+
+#define M3D_OK 0
+#define M3D_ERR_INVALID -1  /* bad argument (shape, NULL, unsupported parameter)        */
+#define M3D_ERR_CUDA -2     /* CUDA runtime error                                       */
+#define M3D_ERR_NO_GPU -3   /* no usable sm_100 device: there is NO CPU fallback        */
+
+enum { M3D_MODEL_PINHOLE = 0, M3D_MODEL_FISHEYE = 1, M3D_MODEL_OMNIDIR = 2 };
+
+/* One camera, the fields of the reference's Camera / FisheyeCamera / OmnidirCamera
+ * (cameras.py:173-189, 339-354, 429-472).
+ *   pinhole : K = `matrix`, dist = `dist` (4, 5, 8 or 12 OpenCV coefficients
+ *             k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]); tilt (tauX, tauY) unsupported
+ *   fisheye : K = `matrix`, dist = `dist` (k1..k4, Kannala-Brandt)
+ *   omnidir : K = `K` (skew K[1] is used), dist = `D` (k1 k2 p1 p2), xi = `xi[0]`      */
+typedef struct m3d_cam {
+  int32_t model;
+  int32_t n_dist;
+  double K[9];     /* row-major 3x3 */
+  double dist[14];
+  double rvec[3];  /* Rodrigues rotation vector (cameras.py:240) */
+  double tvec[3];
+  double xi;
+} m3d_cam;
+
+typedef struct m3d_rig m3d_rig; /* opaque camera group (CameraGroup, cameras.py:558-561) */
+
+int m3d_version(void);
+const char* m3d_last_error(void);
+int m3d_device_count(void); /* number of visible CUDA devices (<=0: product unusable) */
+
+/* CameraGroup(cameras) on GPU `device`.  Rotation matrices are built with the
+ * cv2.Rodrigues formula (utils.py:9-15 make_M). */
+int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig** out);
+void m3d_rig_destroy(m3d_rig* rig);
+int32_t m3d_rig_num_cams(const m3d_rig* rig);
+int32_t m3d_rig_device(const m3d_rig* rig);
+/* Camera.get_extrinsics_mat / make_M for every camera -> host array (C,4,4)
+ * (cameras.py:252, utils.py:9-15). */
+int m3d_rig_extrinsics(const m3d_rig* rig, double* M_host);
+
+/* ---- per-camera maps ------------------------------------------------------------- */
+/* Camera.undistort_points / FisheyeCamera.~ / OmnidirCamera.~ (cameras.py:310,376,498):
+ * xy_dev (n,2) pixels of camera `cam` -> out_dev (n,2) normalised coordinates. */
+int m3d_undistort_cam(const m3d_rig* rig, int32_t cam, const double* xy_dev, int64_t n,
+                      double* out_dev, void* stream);
+/* Camera.project (cameras.py:318,384,509): p3d_dev (n,3) -> out_dev (n,2) pixels. */
+int m3d_project_cam(const m3d_rig* rig, int32_t cam, const double* p3d_dev, int64_t n,
+                    double* out_dev, void* stream);
+/* Camera.distort_points (cameras.py:301,366,487): normalised (n,2) -> pixels (n,2). */
+int m3d_distort_cam(const m3d_rig* rig, int32_t cam, const double* xy_dev, int64_t n,
+                    double* out_dev, void* stream);
+
+/* ---- camera-group maps ------------------------------------------------------------ */
+/* Batched form of the per-camera loop at cameras.py:608-614: xy_dev (C,N,2) -> (C,N,2). */
+int m3d_undistort(const m3d_rig* rig, const double* xy_dev, int64_t N, double* out_dev,
+                  void* stream);
+/* CameraGroup.project (cameras.py:580-591): p3d_dev (N,3) -> out_dev (C,N,2). */
+int m3d_project(const m3d_rig* rig, const double* p3d_dev, int64_t N, double* out_dev,
+                void* stream);
+/* CameraGroup.triangulate (cameras.py:593-637): xy_dev (C,N,2) -> p3d_dev (N,3).
+ * undistort != 0 applies the per-camera undistortion first.  A camera is used for a
+ * point iff its (undistorted) x is not NaN; fewer than two -> (NaN,NaN,NaN). */
+int m3d_triangulate(const m3d_rig* rig, const double* xy_dev, int64_t N, int32_t undistort,
+                    double* p3d_dev, void* stream);
+/* CameraGroup.reprojection_error (cameras.py:746-783): p3d_dev (N,3), xy_dev (C,N,2) raw
+ * pixels.  mean == 0: out_dev (C,N,2) residuals xy - project(p3d).  mean != 0: out_dev (N)
+ * mean residual norm over cameras with a non-NaN residual, NaN when fewer than two. */
+int m3d_reproj_error(const m3d_rig* rig, const double* p3d_dev, const double* xy_dev,
+                     int64_t N, int32_t mean, double* out_dev, void* stream);
+/* Fused triangulate + reprojection_error(mean=True): the plain branch of the 3D stage
+ * (step4_aniposefiltering.py:306-309) in one pass over the input.
+ * err_dev may be NULL. */
+int m3d_triangulate_error(const m3d_rig* rig, const double* xy_dev, int64_t N,
+                          int32_t undistort, double* p3d_dev, double* err_dev, void* stream);
+/* CameraGroup.triangulate_ransac == triangulate_possible with one candidate per camera
+ * (cameras.py:639-743): exhaustive search over camera subsets in itertools.product order
+ * (camera V[j] of the k valid ones is dropped iff bit k-1-j of the step index s is set),
+ * subsets smaller than min_cams skipped unless they are the full valid set, accept when
+ * err < best (best starts at init_best = 200), stop when best < threshold (= 0.5).
+ *   p3d_dev (N,3)          NaN when nothing was selected
+ *   picked_dev (C,N) u8    1 for the cameras of the selected subset      [may be NULL]
+ *   xy_picked_dev (C,N,2)  raw pixels of the selected cameras, else NaN  [may be NULL]
+ *   err_dev (N)            mean reprojection error of the selection, 0.0 when none
+ *   subset_dev (N) i32     step index s of the selection, -1 when none   [may be NULL]
+ *   neval_dev (N) i32      subsets the reference would have triangulated [may be NULL] */
+int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy_dev, int64_t N,
+                           int32_t undistort, int32_t min_cams, double threshold,
+                           double init_best, double* p3d_dev, uint8_t* picked_dev,
+                           double* xy_picked_dev, double* err_dev, int32_t* subset_dev,
+                           int32_t* neval_dev, void* stream);
+
+/* ---- host-buffer pipelines (H2D and D2H inside the call) --------------------------- */
+/* Same results as the _dev calls above; xy_host (C,N,2) etc. live in host memory
+ * (page-locked memory gives full PCIe speed; pageable memory works but is slower). */
+int m3d_triangulate_error_host(const m3d_rig* rig, const double* xy_host, int64_t N,
+                               int32_t undistort, double* p3d_host, double* err_host);
+int m3d_triangulate_ransac_host(const m3d_rig* rig, const double* xy_host, int64_t N,
+                                int32_t undistort, int32_t min_cams, double threshold,
+                                double init_best, double* p3d_host, uint8_t* picked_host,
+                                double* xy_picked_host, double* err_host,
+                                int32_t* subset_host, int32_t* neval_host);
+/* cudaHostRegister / cudaHostUnregister for caller-owned numpy buffers. */
+int m3d_host_register(void* ptr, int64_t bytes);
+int m3d_host_unregister(void* ptr);
+
+/* ---- cross-view association (step2) ------------------------------------------------ */
+/* geometry_affinity2 (step2_crossviewmatching.py:373-432) for F frames at once.
+ *   kp_dev (F,M,J,3)   undistorted x, y and score of every detection, M <= M3D_MAX_DETS
+ *   dim_dev (F,C+1) i32 cumulative detection counts per camera (dimGroup); detections
+ *                      beyond dim[f][C] are padding and give distance 300 / affinity rows
+ *                      that the caller ignores
+ *   aff_dev (F,M,M)    affinity; dist_dev (F,M,M) mean ray distance [may be NULL]
+ * thr_kp = 0.1 (THR_KP, step2:21). */
+int m3d_ray_affinity(const m3d_rig* rig, const double* kp_dev, const int32_t* dim_dev,
+                     int32_t F, int32_t M, int32_t J, double thr_kp, double* aff_dev,
+                     double* dist_dev, void* stream);
+/* mct.triangulatePoints (multicam_toolbox.py:433-486): inhomogeneous least squares
+ * X = -pinv(A[:, :3]) A[:, 3] on already-undistorted points.
+ *   xy_dev (C,N,2), use_dev (C,N) u8 (frame_use transposed), p3d_dev (N,3). */
+int m3d_triangulate_ls(const m3d_rig* rig, const double* xy_dev, const uint8_t* use_dev,
+                       int64_t N, double* p3d_dev, void* stream);
+/* matchSVT (step2_crossviewmatching.py:130-216) with pselect = 1 and
+ * dual_stochastic_SVT = False, F frames at once: W_dev (F,M,M) affinity,
+ * dim_dev (F,C+1) i32, match_dev (F,M,M) u8, iters_dev (F) i32 [may be NULL]. */
+int m3d_match_svt(const double* W_dev, const int32_t* dim_dev, int32_t F, int32_t M,
+                  int32_t C, double alpha, double lambda, double mu, double tol,
+                  int32_t max_iter, uint8_t* match_dev, int32_t* iters_dev, int32_t device,
+                  void* stream);
+
+/* ---- measurement helpers ----------------------------------------------------------- */
+/* Number of kernels this library has launched on the calling process (bench.py's
+ * gpu_launches). */
+int64_t m3d_launch_count(void);
+/* fp64 FMA peak probe: runs a dependent-chain DFMA kernel and returns TFLOP/s. */
+int m3d_probe_fp64_tflops(int32_t device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3D_H_ */

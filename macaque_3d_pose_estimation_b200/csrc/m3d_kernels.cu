@@ -1,0 +1,913 @@
+// m3d_kernels.cu — sm_100a kernels and the C ABI (include/m3d.h) of the multi-view 3D
+// reconstruction hot path.  No tensor cores (largest matrix on the path is 4x4 per
+// point); the work is fp64 ALU + HBM streaming:
+//   * one thread per joint-instance for undistort / DLT / reprojection error, 16-byte
+//     vector loads of the (C,N,2) observation planes (each camera plane is read fully
+//     coalesced: 512 B per warp per camera);
+//   * the camera rig (<= 16 cameras, 4.2 KB) travels as a __grid_constant__ kernel
+//     parameter, i.e. it sits in the constant bank and is read with uniform LDC /
+//     constant operands — no global state, no per-launch upload;
+//   * subset RANSAC: lane-per-point evaluation of the full camera set, then one warp per
+//     surviving point with one camera subset per lane (32 subsets per step), __ballot_sync
+//     + __ffs for "first subset under the threshold", shuffle arg-min otherwise.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/m3d.h"
+#include "m3d_internal.h"
+#include "m3d_math.cuh"
+#include "m3d_point.cuh"
+#include "m3d_rig.h"
+
+using namespace m3d;
+
+// ---------------------------------------------------------------------------------------
+// error handling / bookkeeping
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+int m3d_fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+static int fail(int code, const std::string& msg) { return m3d_fail(code, msg); }
+
+#define M3D_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(M3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+struct m3d_rig {
+  RigDev dev;
+  int device;
+  // workspace of the *_host pipelines (lazily allocated, guarded by ws_mutex)
+  std::mutex ws_mutex;
+  static const int kSlots = 3;
+  int64_t ws_chunk = 0;
+  int ws_cams = 0;
+  double* ws_xy[kSlots] = {nullptr, nullptr, nullptr};
+  double* ws_p3d[kSlots] = {nullptr, nullptr, nullptr};
+  double* ws_err[kSlots] = {nullptr, nullptr, nullptr};
+  double* ws_xyp[kSlots] = {nullptr, nullptr, nullptr};
+  uint8_t* ws_picked[kSlots] = {nullptr, nullptr, nullptr};
+  int32_t* ws_subset[kSlots] = {nullptr, nullptr, nullptr};
+  int32_t* ws_neval[kSlots] = {nullptr, nullptr, nullptr};
+  cudaStream_t ws_stream[kSlots] = {nullptr, nullptr, nullptr};
+  bool ws_ransac = false;
+};
+
+typedef M3dDeviceGuard DeviceGuard;
+
+const RigDev* m3d_rig_dev(const m3d_rig* rig) { return &rig->dev; }
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld_xy(const double* __restrict__ xy, int64_t idx) {
+  // 16-byte read-only load of one (x, y) observation
+  return __ldg(reinterpret_cast<const double2*>(xy) + idx);
+}
+
+__device__ __forceinline__ void st_xy(double* out, int64_t idx, double x, double y) {
+  reinterpret_cast<double2*>(out)[idx] = make_double2(x, y);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: undistort (C,N,2) -> (C,N,2); blockIdx.y selects the camera
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO>
+__global__ void __launch_bounds__(256)
+k_undistort(const __grid_constant__ RigDev rig, int cam0, const double* __restrict__ xy,
+            int64_t N, double* __restrict__ out) {
+  const int c = cam0 + blockIdx.y;
+  const int64_t plane = (int64_t)blockIdx.y * N;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 p = ld_xy(xy, plane + n);
+    double x, y;
+    undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+    st_xy(out, plane + n, x, y);
+  }
+}
+
+// Camera.distort_points for one camera: normalised (n,2) -> pixels (n,2)
+template <bool FULL>
+__global__ void __launch_bounds__(256)
+k_distort(const __grid_constant__ RigDev rig, int cam, const double* __restrict__ xy, int64_t N,
+          double* __restrict__ out) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 p = ld_xy(xy, n);
+    double u, v;
+    distort_point<FULL>(rig.cam[cam], p.x, p.y, u, v);
+    st_xy(out, n, u, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K-project: (N,3) -> (n_out_cams,N,2); one thread per point, loop over cameras
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO>
+__global__ void __launch_bounds__(256)
+k_project(const __grid_constant__ RigDev rig, int cam0, int ncam, const double* __restrict__ p3d,
+          int64_t N, double* __restrict__ out) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const double X = __ldg(p3d + 3 * n), Y = __ldg(p3d + 3 * n + 1), Z = __ldg(p3d + 3 * n + 2);
+#pragma unroll 1
+    for (int j = 0; j < ncam; ++j) {
+      double u, v;
+      project_point<FULL, PO>(rig.cam[cam0 + j], X, Y, Z, u, v);
+      st_xy(out, (int64_t)j * N + n, u, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: fused undistort + DLT triangulation (+ mean reprojection error)
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO, bool UNDISTORT, bool WITH_ERR>
+__global__ void __launch_bounds__(256)
+k_triangulate(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t N,
+              double* __restrict__ p3d, double* __restrict__ err) {
+  const int C = rig.n_cams;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    Gram G;
+    gram_zero(G);
+    int cnt = 0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const double2 p = ld_xy(xy, (int64_t)c * N + n);
+      double x = p.x, y = p.y;
+      if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+      if (x == x) {  // validity on x only (cameras.py:630)
+        gram_add_camera(G, rig.cam[c], x, y);
+        ++cnt;
+      }
+    }
+    double X = qnan(), Y = qnan(), Z = qnan();
+    if (cnt >= 2) dlt_solve(G, X, Y, Z);
+    p3d[3 * n] = X;
+    p3d[3 * n + 1] = Y;
+    p3d[3 * n + 2] = Z;
+    if (WITH_ERR) {
+      double sum = 0.0;
+      int m = 0;
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        const double2 p = ld_xy(xy, (int64_t)c * N + n);
+        double u, v;
+        project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
+        const double e = residual_norm(p.x - u, p.y - v);
+        if (e == e) {
+          sum += e;
+          ++m;
+        }
+      }
+      err[n] = (m >= 2) ? sum / (double)m : qnan();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: reprojection error, full residuals (C,N,2) or mean (N)
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO, bool MEAN>
+__global__ void __launch_bounds__(256)
+k_reproj(const __grid_constant__ RigDev rig, const double* __restrict__ p3d,
+         const double* __restrict__ xy, int64_t N, double* __restrict__ out) {
+  const int C = rig.n_cams;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const double X = __ldg(p3d + 3 * n), Y = __ldg(p3d + 3 * n + 1), Z = __ldg(p3d + 3 * n + 2);
+    double sum = 0.0;
+    int m = 0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const double2 p = ld_xy(xy, (int64_t)c * N + n);
+      double u, v;
+      project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
+      const double ex = p.x - u, ey = p.y - v;
+      if (MEAN) {
+        const double e = residual_norm(ex, ey);
+        if (e == e) {
+          sum += e;
+          ++m;
+        }
+      } else {
+        st_xy(out, (int64_t)c * N + n, ex, ey);
+      }
+    }
+    if (MEAN) out[n] = (m >= 2) ? sum / (double)m : qnan();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K7: inhomogeneous least-squares triangulation (mct.triangulatePoints)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
+                 const uint8_t* __restrict__ use, int64_t N, double* __restrict__ p3d) {
+  const int C = rig.n_cams;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    Gram G;
+    gram_zero(G);
+    int cnt = 0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      if (use[(int64_t)c * N + n]) {
+        const double2 p = ld_xy(xy, (int64_t)c * N + n);
+        gram_add_camera(G, rig.cam[c], p.x, p.y);
+        ++cnt;
+      }
+    }
+    double X = qnan(), Y = qnan(), Z = qnan();
+    if (cnt >= 2) ls_solve(G, X, Y, Z);
+    p3d[3 * n] = X;
+    p3d[3 * n + 1] = Y;
+    p3d[3 * n + 2] = Z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: camera-subset RANSAC (triangulate_possible with one candidate per camera)
+// ---------------------------------------------------------------------------------------
+constexpr int RANSAC_WARPS = 4;
+
+struct WarpScratch {
+  double raw[2 * M3D_MAXC];  // raw pixels of the current point, per camera
+  Gram gc[M3D_MAXC];         // per-camera Gram contribution of the current point
+};
+
+template <bool FULL, bool PO>
+__global__ void __launch_bounds__(RANSAC_WARPS * 32)
+k_ransac(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t N,
+         int undistort, int min_cams, double thr, double init_best, double* __restrict__ p3d,
+         uint8_t* __restrict__ picked, double* __restrict__ xy_picked, double* __restrict__ err_out,
+         int32_t* __restrict__ subset_out, int32_t* __restrict__ neval_out) {
+  __shared__ WarpScratch scratch[RANSAC_WARPS];
+  const unsigned FULLM = 0xffffffffu;
+  const int C = rig.n_cams;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpScratch& ws = scratch[warp];
+  const int64_t tile0 = ((int64_t)blockIdx.x * RANSAC_WARPS + warp) * 32;
+  if (tile0 >= N) return;
+  const int64_t n = tile0 + lane;
+  const bool inb = n < N;
+  // first subset whose error is below T1 wins (see DESIGN.md "subset search")
+  const double T1 = thr < init_best ? thr : init_best;
+
+  // ---- phase A: lane = point; evaluate s = 0 (all valid cameras) -------------------------
+  uint32_t vmask = 0, umask = 0;
+  double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
+  int32_t best_s = -1, neval = 0;
+  uint32_t best_mask = 0;
+  bool done = !inb;
+  if (inb) {
+    Gram G;
+    gram_zero(G);
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const double2 p = ld_xy(xy, (int64_t)c * N + n);
+      if (p.x == p.x) {  // validity on the RAW x (cameras.py:658-659)
+        vmask |= 1u << c;
+        double x = p.x, y = p.y;
+        if (undistort) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+        if (x == x) {  // survives inside triangulate (cameras.py:630)
+          umask |= 1u << c;
+          gram_add_camera(G, rig.cam[c], x, y);
+        }
+      }
+    }
+    const int k = __popc(vmask);
+    neval = 1;  // the full set is always tried (cameras.py:691)
+    if (__popc(umask) >= 2) {
+      double X, Y, Z;
+      dlt_solve(G, X, Y, Z);
+      double sum = 0.0;
+      int m = 0;
+      for (uint32_t rest = vmask; rest; rest &= rest - 1) {
+        const int c = __ffs(rest) - 1;
+        const double2 p = ld_xy(xy, (int64_t)c * N + n);
+        double u, v;
+        project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
+        const double e = residual_norm(p.x - u, p.y - v);
+        if (e == e) {
+          sum += e;
+          ++m;
+        }
+      }
+      const double e0 = (m >= 2) ? sum / (double)m : qnan();
+      if (e0 < best_err) {
+        best_err = e0;
+        best_s = 0;
+        best_mask = vmask;
+        bx = X;
+        by = Y;
+        bz = Z;
+        if (e0 < thr) done = true;
+      }
+    }
+    // every smaller subset is skipped when k <= min_cams (or k < 2: nothing to drop)
+    if (k < 2 || k <= min_cams) done = true;
+  }
+
+  // ---- phase B: one warp per unfinished point, one subset per lane ------------------------
+  uint32_t todo = __ballot_sync(FULLM, !done);
+  while (todo) {
+    const int p = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int64_t np = tile0 + p;
+    const uint32_t vm = __shfl_sync(FULLM, vmask, p);
+    const uint32_t um = __shfl_sync(FULLM, umask, p);
+    const int k = __popc(vm);
+    const uint32_t n_sub = 1u << k;
+    __syncwarp();
+    if (lane < C) {
+      const double2 q = ld_xy(xy, (int64_t)lane * N + np);
+      ws.raw[2 * lane] = q.x;
+      ws.raw[2 * lane + 1] = q.y;
+      Gram g;
+      gram_zero(g);
+      if ((um >> lane) & 1u) {
+        double x = q.x, y = q.y;
+        if (undistort) undistort_point<FULL, PO>(rig.cam[lane], q.x, q.y, x, y);
+        gram_add_camera(g, rig.cam[lane], x, y);
+      }
+      ws.gc[lane] = g;
+    }
+    __syncwarp();
+
+    // pass 1: first admissible s >= 1 with err < T1
+    bool found = false;
+    int32_t ne = 0;
+    for (uint32_t base = 0; base < n_sub; base += 32) {
+      const uint32_t s = base + lane;
+      uint32_t cm = 0;
+      bool adm = false;
+      if (s >= 1 && s < n_sub) {
+        cm = subset_mask(vm, k, s);
+        const int cnt = __popc(cm);
+        adm = (cnt >= min_cams) || (cnt == k);
+      }
+      double X = qnan(), Y = qnan(), Z = qnan(), e = pos_inf();
+      if (adm) e = eval_subset<FULL, PO>(rig, ws.raw, ws.gc, cm, um, T1, X, Y, Z);
+      const uint32_t hit = __ballot_sync(FULLM, adm && (e < T1));
+      const uint32_t admb = __ballot_sync(FULLM, adm);
+      if (hit) {
+        const int wl = __ffs(hit) - 1;
+        ne += __popc(admb & (0xffffffffu >> (31 - wl)));
+        const double we = __shfl_sync(FULLM, e, wl);
+        const double wx = __shfl_sync(FULLM, X, wl);
+        const double wy = __shfl_sync(FULLM, Y, wl);
+        const double wz = __shfl_sync(FULLM, Z, wl);
+        const uint32_t wm = __shfl_sync(FULLM, cm, wl);
+        if (lane == p) {
+          best_err = we;
+          best_s = (int32_t)(base + wl);
+          best_mask = wm;
+          bx = wx;
+          by = wy;
+          bz = wz;
+        }
+        found = true;
+        break;
+      }
+      ne += __popc(admb);
+    }
+    if (lane == p) neval += ne;
+    if (found) continue;
+
+    // pass 2 (no subset under T1): strict arg-min over all admissible subsets, first wins
+    // on ties; pruning against the running best keeps it exact.
+    double rb = __shfl_sync(FULLM, best_err, p);
+    for (uint32_t base = 0; base < n_sub; base += 32) {
+      const uint32_t s = base + lane;
+      uint32_t cm = 0;
+      bool adm = false;
+      if (s >= 1 && s < n_sub) {
+        cm = subset_mask(vm, k, s);
+        const int cnt = __popc(cm);
+        adm = (cnt >= min_cams) || (cnt == k);
+      }
+      double X = qnan(), Y = qnan(), Z = qnan(), e = pos_inf();
+      if (adm) e = eval_subset<FULL, PO>(rig, ws.raw, ws.gc, cm, um, rb, X, Y, Z);
+      if (!(e < rb)) e = pos_inf();  // NaN / pruned / not better
+      // warp arg-min on (e, lane): lowest lane wins ties
+      double me = e;
+      int ml = lane;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double oe = __shfl_xor_sync(FULLM, me, off);
+        const int ol = __shfl_xor_sync(FULLM, ml, off);
+        if (oe < me || (oe == me && ol < ml)) {
+          me = oe;
+          ml = ol;
+        }
+      }
+      if (me < rb) {
+        rb = me;
+        const double wx = __shfl_sync(FULLM, X, ml);
+        const double wy = __shfl_sync(FULLM, Y, ml);
+        const double wz = __shfl_sync(FULLM, Z, ml);
+        const uint32_t wm = __shfl_sync(FULLM, cm, ml);
+        if (lane == p) {
+          best_err = me;
+          best_s = (int32_t)(base + ml);
+          best_mask = wm;
+          bx = wx;
+          by = wy;
+          bz = wz;
+        }
+      }
+    }
+  }
+
+  // ---- outputs: lane = point again, coalesced per plane -------------------------------------
+  if (inb) {
+    p3d[3 * n] = bx;
+    p3d[3 * n + 1] = by;
+    p3d[3 * n + 2] = bz;
+    err_out[n] = (best_s >= 0) ? best_err : 0.0;  // errors default to 0.0 (cameras.py:675)
+    if (subset_out) subset_out[n] = best_s;
+    if (neval_out) neval_out[n] = neval;
+    if (picked || xy_picked) {
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        const bool in = (best_mask >> c) & 1u;
+        if (picked) picked[(int64_t)c * N + n] = in ? 1 : 0;
+        if (xy_picked) {
+          double2 q = make_double2(qnan(), qnan());
+          if (in) q = ld_xy(xy, (int64_t)c * N + n);
+          st_xy(xy_picked, (int64_t)c * N + n, q.x, q.y);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 FMA peak probe (the second roofline of this path)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, b);
+    a1 = fma(a1, m, b);
+    a2 = fma(a2, m, b);
+    a3 = fma(a3, m, b);
+    a4 = fma(a4, m, b);
+    a5 = fma(a5, m, b);
+    a6 = fma(a6, m, b);
+    a7 = fma(a7, m, b);
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+static int grid_for(int64_t N, int threads, int sm_count) {
+  // grid-stride kernels: enough blocks to cover N, capped at 32 waves of resident blocks
+  int64_t blocks = (N + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count * 8 * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static int sm_count_of(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int v = 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  if (device >= 0 && device < 64) cached[device] = v;
+  return v;
+}
+
+#define M3D_DISPATCH_MODEL(rig, CALL)                                      \
+  do {                                                                     \
+    const bool full__ = ((rig)->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM)) != 0; \
+    const bool po__ = ((rig)->dev.flags & RIG_HAS_NONPINHOLE) == 0;        \
+    if (full__) {                                                          \
+      if (po__) { CALL(true, true); } else { CALL(true, false); }          \
+    } else {                                                               \
+      if (po__) { CALL(false, true); } else { CALL(false, false); }        \
+    }                                                                      \
+  } while (0)
+
+int m3d_check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(M3D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return M3D_OK;
+}
+static int check_launch(const char* what) { return m3d_check_launch(what); }
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int m3d_version(void) { return 100; }
+
+const char* m3d_last_error(void) { return g_last_error.c_str(); }
+
+int m3d_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t m3d_launch_count(void) { return g_launches.load(); }
+
+int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig** out) {
+  if (!out) return fail(M3D_ERR_INVALID, "m3d_rig_create: out is NULL");
+  *out = nullptr;
+  int ndev = m3d_device_count();
+  if (ndev <= 0)
+    return fail(M3D_ERR_NO_GPU, "m3d_rig_create: no CUDA device visible; libm3d has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(M3D_ERR_INVALID, "m3d_rig_create: bad device index");
+  m3d_rig* rig = new m3d_rig();
+  std::string why = build_rig(cams, n_cams, &rig->dev);
+  if (!why.empty()) {
+    delete rig;
+    return fail(M3D_ERR_INVALID, "m3d_rig_create: " + why);
+  }
+  rig->device = device;
+  *out = rig;
+  return M3D_OK;
+}
+
+static void free_workspace(m3d_rig* rig) {
+  for (int i = 0; i < m3d_rig::kSlots; ++i) {
+    cudaFree(rig->ws_xy[i]);
+    cudaFree(rig->ws_p3d[i]);
+    cudaFree(rig->ws_err[i]);
+    cudaFree(rig->ws_xyp[i]);
+    cudaFree(rig->ws_picked[i]);
+    cudaFree(rig->ws_subset[i]);
+    cudaFree(rig->ws_neval[i]);
+    rig->ws_xy[i] = rig->ws_p3d[i] = rig->ws_err[i] = rig->ws_xyp[i] = nullptr;
+    rig->ws_picked[i] = nullptr;
+    rig->ws_subset[i] = rig->ws_neval[i] = nullptr;
+    if (rig->ws_stream[i]) cudaStreamDestroy(rig->ws_stream[i]);
+    rig->ws_stream[i] = nullptr;
+  }
+  rig->ws_chunk = 0;
+}
+
+void m3d_rig_destroy(m3d_rig* rig) {
+  if (!rig) return;
+  {
+    DeviceGuard g(rig->device);
+    free_workspace(rig);
+  }
+  delete rig;
+}
+
+int32_t m3d_rig_num_cams(const m3d_rig* rig) { return rig ? rig->dev.n_cams : -1; }
+int32_t m3d_rig_device(const m3d_rig* rig) { return rig ? rig->device : -1; }
+
+int m3d_rig_extrinsics(const m3d_rig* rig, double* M) {
+  if (!rig || !M) return fail(M3D_ERR_INVALID, "m3d_rig_extrinsics: NULL argument");
+  for (int c = 0; c < rig->dev.n_cams; ++c) {
+    const CamDev& cam = rig->dev.cam[c];
+    double* o = M + 16 * c;
+    for (int r = 0; r < 3; ++r) {
+      o[4 * r + 0] = cam.R[3 * r + 0];
+      o[4 * r + 1] = cam.R[3 * r + 1];
+      o[4 * r + 2] = cam.R[3 * r + 2];
+      o[4 * r + 3] = cam.t[r];
+    }
+    o[12] = o[13] = o[14] = 0.0;
+    o[15] = 1.0;
+  }
+  return M3D_OK;
+}
+
+#define M3D_CHECK_RIG(name)                                              \
+  if (!rig) return fail(M3D_ERR_INVALID, name ": rig is NULL");          \
+  if (N < 0) return fail(M3D_ERR_INVALID, name ": negative point count"); \
+  DeviceGuard guard__(rig->device);                                      \
+  cudaStream_t st = (cudaStream_t)stream;                                \
+  const int sms = sm_count_of(rig->device);                              \
+  (void)sms;
+
+int m3d_undistort_cam(const m3d_rig* rig, int32_t cam, const double* xy, int64_t N, double* out,
+                      void* stream) {
+  M3D_CHECK_RIG("m3d_undistort_cam");
+  if (cam < 0 || cam >= rig->dev.n_cams) return fail(M3D_ERR_INVALID, "m3d_undistort_cam: bad camera index");
+  if (N == 0) return M3D_OK;
+  if (!xy || !out) return fail(M3D_ERR_INVALID, "m3d_undistort_cam: NULL buffer");
+  dim3 grid(grid_for(N, 256, sms), 1);
+#define CALL(F, P) k_undistort<F, P><<<grid, 256, 0, st>>>(rig->dev, cam, xy, N, out)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_undistort");
+}
+
+int m3d_undistort(const m3d_rig* rig, const double* xy, int64_t N, double* out, void* stream) {
+  M3D_CHECK_RIG("m3d_undistort");
+  if (N == 0 || rig->dev.n_cams == 0) return M3D_OK;
+  if (!xy || !out) return fail(M3D_ERR_INVALID, "m3d_undistort: NULL buffer");
+  dim3 grid(grid_for(N, 256, sms), rig->dev.n_cams);
+#define CALL(F, P) k_undistort<F, P><<<grid, 256, 0, st>>>(rig->dev, 0, xy, N, out)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_undistort");
+}
+
+int m3d_distort_cam(const m3d_rig* rig, int32_t cam, const double* xy, int64_t N, double* out,
+                    void* stream) {
+  M3D_CHECK_RIG("m3d_distort_cam");
+  if (cam < 0 || cam >= rig->dev.n_cams) return fail(M3D_ERR_INVALID, "m3d_distort_cam: bad camera index");
+  if (N == 0) return M3D_OK;
+  if (!xy || !out) return fail(M3D_ERR_INVALID, "m3d_distort_cam: NULL buffer");
+  const int grid = grid_for(N, 256, sms);
+  if (rig->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM))
+    k_distort<true><<<grid, 256, 0, st>>>(rig->dev, cam, xy, N, out);
+  else
+    k_distort<false><<<grid, 256, 0, st>>>(rig->dev, cam, xy, N, out);
+  return check_launch("k_distort");
+}
+
+int m3d_project_cam(const m3d_rig* rig, int32_t cam, const double* p3d, int64_t N, double* out,
+                    void* stream) {
+  M3D_CHECK_RIG("m3d_project_cam");
+  if (cam < 0 || cam >= rig->dev.n_cams) return fail(M3D_ERR_INVALID, "m3d_project_cam: bad camera index");
+  if (N == 0) return M3D_OK;
+  if (!p3d || !out) return fail(M3D_ERR_INVALID, "m3d_project_cam: NULL buffer");
+  const int grid = grid_for(N, 256, sms);
+#define CALL(F, P) k_project<F, P><<<grid, 256, 0, st>>>(rig->dev, cam, 1, p3d, N, out)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_project");
+}
+
+int m3d_project(const m3d_rig* rig, const double* p3d, int64_t N, double* out, void* stream) {
+  M3D_CHECK_RIG("m3d_project");
+  if (N == 0 || rig->dev.n_cams == 0) return M3D_OK;
+  if (!p3d || !out) return fail(M3D_ERR_INVALID, "m3d_project: NULL buffer");
+  const int grid = grid_for(N, 256, sms);
+#define CALL(F, P) k_project<F, P><<<grid, 256, 0, st>>>(rig->dev, 0, rig->dev.n_cams, p3d, N, out)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_project");
+}
+
+static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, int undistort,
+                              double* p3d, double* err, cudaStream_t st, int sms) {
+  const int grid = grid_for(N, 256, sms);
+#define CALL(F, P)                                                                          \
+  do {                                                                                      \
+    if (undistort) {                                                                        \
+      if (err) k_triangulate<F, P, true, true><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
+      else k_triangulate<F, P, true, false><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);    \
+    } else {                                                                                \
+      if (err) k_triangulate<F, P, false, true><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
+      else k_triangulate<F, P, false, false><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);   \
+    }                                                                                       \
+  } while (0)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_triangulate");
+}
+
+int m3d_triangulate(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort, double* p3d,
+                    void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate");
+  if (N == 0) return M3D_OK;
+  if (!p3d || (!xy && rig->dev.n_cams > 0)) return fail(M3D_ERR_INVALID, "m3d_triangulate: NULL buffer");
+  return launch_triangulate(rig, xy, N, undistort, p3d, nullptr, st, sms);
+}
+
+int m3d_triangulate_error(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
+                          double* p3d, double* err, void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate_error");
+  if (N == 0) return M3D_OK;
+  if (!p3d || (!xy && rig->dev.n_cams > 0))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_error: NULL buffer");
+  return launch_triangulate(rig, xy, N, undistort, p3d, err, st, sms);
+}
+
+int m3d_reproj_error(const m3d_rig* rig, const double* p3d, const double* xy, int64_t N,
+                     int32_t mean, double* out, void* stream) {
+  M3D_CHECK_RIG("m3d_reproj_error");
+  if (N == 0) return M3D_OK;
+  if (!p3d || !out || (!xy && rig->dev.n_cams > 0))
+    return fail(M3D_ERR_INVALID, "m3d_reproj_error: NULL buffer");
+  if (!mean && rig->dev.n_cams == 0) return M3D_OK;
+  const int grid = grid_for(N, 256, sms);
+#define CALL(F, P)                                                                     \
+  do {                                                                                 \
+    if (mean) k_reproj<F, P, true><<<grid, 256, 0, st>>>(rig->dev, p3d, xy, N, out);   \
+    else k_reproj<F, P, false><<<grid, 256, 0, st>>>(rig->dev, p3d, xy, N, out);       \
+  } while (0)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_reproj");
+}
+
+static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int undistort, int min_cams,
+                         double threshold, double init_best, double* p3d, uint8_t* picked,
+                         double* xy_picked, double* err, int32_t* subset, int32_t* neval,
+                         cudaStream_t st) {
+  const int64_t per_block = RANSAC_WARPS * 32;
+  const int64_t blocks = (N + per_block - 1) / per_block;
+  if (blocks > 0x7fffffffLL) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: N too large for one launch");
+#define CALL(F, P)                                                                              \
+  k_ransac<F, P><<<(unsigned)blocks, RANSAC_WARPS * 32, 0, st>>>(rig->dev, xy, N, undistort, min_cams, \
+                                                                 threshold, init_best, p3d, picked,    \
+                                                                 xy_picked, err, subset, neval)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_ransac");
+}
+
+int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
+                           int32_t min_cams, double threshold, double init_best, double* p3d,
+                           uint8_t* picked, double* xy_picked, double* err, int32_t* subset,
+                           int32_t* neval, void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate_ransac");
+  if (N == 0) return M3D_OK;
+  if (!p3d || !err || (!xy && rig->dev.n_cams > 0))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: NULL buffer");
+  return launch_ransac(rig, xy, N, undistort, min_cams, threshold, init_best, p3d, picked, xy_picked,
+                       err, subset, neval, st);
+}
+
+int m3d_triangulate_ls(const m3d_rig* rig, const double* xy, const uint8_t* use, int64_t N,
+                       double* p3d, void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate_ls");
+  if (N == 0) return M3D_OK;
+  if (!p3d || ((!xy || !use) && rig->dev.n_cams > 0))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ls: NULL buffer");
+  k_triangulate_ls<<<grid_for(N, 256, sms), 256, 0, st>>>(rig->dev, xy, use, N, p3d);
+  return check_launch("k_triangulate_ls");
+}
+
+// ---- host pipelines ------------------------------------------------------------------------
+static int ensure_workspace(m3d_rig* rig, int64_t chunk, bool ransac) {
+  const int C = rig->dev.n_cams > 0 ? rig->dev.n_cams : 1;
+  if (rig->ws_chunk >= chunk && rig->ws_cams == C && (rig->ws_ransac || !ransac)) return M3D_OK;
+  free_workspace(rig);
+  for (int i = 0; i < m3d_rig::kSlots; ++i) {
+    M3D_CUDA(cudaStreamCreateWithFlags(&rig->ws_stream[i], cudaStreamNonBlocking));
+    M3D_CUDA(cudaMalloc(&rig->ws_xy[i], sizeof(double) * 2 * C * chunk));
+    M3D_CUDA(cudaMalloc(&rig->ws_p3d[i], sizeof(double) * 3 * chunk));
+    M3D_CUDA(cudaMalloc(&rig->ws_err[i], sizeof(double) * chunk));
+    if (ransac) {
+      M3D_CUDA(cudaMalloc(&rig->ws_xyp[i], sizeof(double) * 2 * C * chunk));
+      M3D_CUDA(cudaMalloc(&rig->ws_picked[i], (size_t)C * chunk));
+      M3D_CUDA(cudaMalloc(&rig->ws_subset[i], sizeof(int32_t) * chunk));
+      M3D_CUDA(cudaMalloc(&rig->ws_neval[i], sizeof(int32_t) * chunk));
+    }
+  }
+  rig->ws_chunk = chunk;
+  rig->ws_cams = C;
+  rig->ws_ransac = ransac;
+  return M3D_OK;
+}
+
+static const int64_t kHostChunk = 1 << 19;  // joint-instances per pipeline stage
+
+static int host_pipeline(m3d_rig* rig, const double* xy, int64_t N, int undistort, bool ransac,
+                         int min_cams, double threshold, double init_best, double* p3d,
+                         uint8_t* picked, double* xy_picked, double* err, int32_t* subset,
+                         int32_t* neval) {
+  if (N == 0) return M3D_OK;
+  DeviceGuard guard(rig->device);
+  std::lock_guard<std::mutex> lock(rig->ws_mutex);
+  const int C = rig->dev.n_cams;
+  const int64_t chunk = N < kHostChunk ? N : kHostChunk;
+  int rc = ensure_workspace(rig, chunk, ransac);
+  if (rc) return rc;
+  const int sms = sm_count_of(rig->device);
+  int64_t done = 0;
+  for (int it = 0; done < N; ++it) {
+    const int slot = it % m3d_rig::kSlots;
+    cudaStream_t st = rig->ws_stream[slot];
+    const int64_t n = (N - done) < chunk ? (N - done) : chunk;
+    // the slot's previous D2H copies must have left its buffers (same stream => ordered)
+    if (C > 0)
+      M3D_CUDA(cudaMemcpy2DAsync(rig->ws_xy[slot], sizeof(double) * 2 * n, xy + 2 * done,
+                                 sizeof(double) * 2 * N, sizeof(double) * 2 * n, C,
+                                 cudaMemcpyHostToDevice, st));
+    if (!ransac) {
+      rc = launch_triangulate(rig, rig->ws_xy[slot], n, undistort, rig->ws_p3d[slot],
+                              err ? rig->ws_err[slot] : nullptr, st, sms);
+      if (rc) return rc;
+    } else {
+      rc = launch_ransac(rig, rig->ws_xy[slot], n, undistort, min_cams, threshold, init_best,
+                         rig->ws_p3d[slot], picked ? rig->ws_picked[slot] : nullptr,
+                         xy_picked ? rig->ws_xyp[slot] : nullptr, rig->ws_err[slot],
+                         subset ? rig->ws_subset[slot] : nullptr, neval ? rig->ws_neval[slot] : nullptr, st);
+      if (rc) return rc;
+    }
+    M3D_CUDA(cudaMemcpyAsync(p3d + 3 * done, rig->ws_p3d[slot], sizeof(double) * 3 * n,
+                             cudaMemcpyDeviceToHost, st));
+    if (err)
+      M3D_CUDA(cudaMemcpyAsync(err + done, rig->ws_err[slot], sizeof(double) * n,
+                               cudaMemcpyDeviceToHost, st));
+    if (ransac) {
+      if (picked && C > 0)
+        M3D_CUDA(cudaMemcpy2DAsync(picked + done, (size_t)N, rig->ws_picked[slot], (size_t)n, (size_t)n,
+                                   C, cudaMemcpyDeviceToHost, st));
+      if (xy_picked && C > 0)
+        M3D_CUDA(cudaMemcpy2DAsync(xy_picked + 2 * done, sizeof(double) * 2 * N, rig->ws_xyp[slot],
+                                   sizeof(double) * 2 * n, sizeof(double) * 2 * n, C,
+                                   cudaMemcpyDeviceToHost, st));
+      if (subset)
+        M3D_CUDA(cudaMemcpyAsync(subset + done, rig->ws_subset[slot], sizeof(int32_t) * n,
+                                 cudaMemcpyDeviceToHost, st));
+      if (neval)
+        M3D_CUDA(cudaMemcpyAsync(neval + done, rig->ws_neval[slot], sizeof(int32_t) * n,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    done += n;
+  }
+  for (int i = 0; i < m3d_rig::kSlots; ++i) M3D_CUDA(cudaStreamSynchronize(rig->ws_stream[i]));
+  return M3D_OK;
+}
+
+int m3d_triangulate_error_host(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
+                               double* p3d, double* err) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host: rig is NULL");
+  if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host: negative point count");
+  if (N > 0 && (!p3d || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, N, undistort, false, 0, 0, 0, p3d, nullptr,
+                       nullptr, err, nullptr, nullptr);
+}
+
+int m3d_triangulate_ransac_host(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
+                                int32_t min_cams, double threshold, double init_best, double* p3d,
+                                uint8_t* picked, double* xy_picked, double* err, int32_t* subset,
+                                int32_t* neval) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host: rig is NULL");
+  if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host: negative point count");
+  if (N > 0 && (!p3d || !err || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, N, undistort, true, min_cams, threshold,
+                       init_best, p3d, picked, xy_picked, err, subset, neval);
+}
+
+int m3d_host_register(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail(M3D_ERR_INVALID, "m3d_host_register: bad buffer");
+  M3D_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return M3D_OK;
+}
+
+int m3d_host_unregister(void* ptr) {
+  if (!ptr) return fail(M3D_ERR_INVALID, "m3d_host_unregister: NULL");
+  M3D_CUDA(cudaHostUnregister(ptr));
+  return M3D_OK;
+}
+
+int m3d_probe_fp64_tflops(int32_t device, double* tflops_out) {
+  if (!tflops_out) return fail(M3D_ERR_INVALID, "m3d_probe_fp64_tflops: NULL");
+  if (m3d_device_count() <= 0) return fail(M3D_ERR_NO_GPU, "m3d_probe_fp64_tflops: no CUDA device");
+  DeviceGuard guard(device);
+  const int sms = sm_count_of(device);
+  const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+  double* buf = nullptr;
+  M3D_CUDA(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  M3D_CUDA(cudaEventCreate(&e0));
+  M3D_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    M3D_CUDA(cudaEventRecord(e0));
+    k_dfma_probe<<<blocks, threads>>>(buf, iters);
+    g_launches.fetch_add(1);
+    M3D_CUDA(cudaEventRecord(e1));
+    M3D_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    M3D_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return M3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// m3d_math.cuh — per-point arithmetic of the hot path (camera maps, DLT solve,
+// reprojection error).  Every function is __host__ __device__ so that the test-only
+// host harness (tests/host_harness.cpp) can compile the SAME source with g++ and check
+// it against the oracle without a GPU; the product only ever runs the device build.
+//
+// Reference semantics (file:line under /root/reference/src/third_party/aniposelib/):
+//   Camera.undistort_points  cameras.py:310  cv2.undistortPoints, 5 fixed-point iterations
+//   Camera.project           cameras.py:318  cv2.projectPoints
+//   FisheyeCamera.*          cameras.py:376,384
+//   OmnidirCamera.*          cameras.py:498,509  (opencv_contrib ccalib; parity unpinned)
+//   triangulate_simple       cameras.py:20-32  DLT rows + smallest right singular vector
+//   reprojection_error       cameras.py:746-783
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define M3D_HD __host__ __device__ __forceinline__
+#define M3D_HD_NOINLINE inline __host__ __device__ __noinline__
+#else
+#define M3D_HD inline
+#define M3D_HD_NOINLINE inline
+#endif
+
+#define M3D_MAXC 16
+
+namespace m3d {
+
+enum { PINHOLE = 0, FISHEYE = 1, OMNIDIR = 2 };
+// rig-level feature flags (select leaner kernel instantiations)
+enum { RIG_HAS_RATIONAL = 1, RIG_HAS_PRISM = 2, RIG_HAS_NONPINHOLE = 4 };
+
+struct CamDev {
+  double fx, fy, cx, cy, skew;
+  double ifx, ify;  // OpenCV multiplies by 1/fx, 1/fy in undistortPoints
+  double k[12];     // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 | fisheye k1..k4 | omnidir k1 k2 p1 p2
+  double R[9];      // row-major rotation (cv2.Rodrigues of rvec)
+  double t[3];
+  double xi;
+  int32_t model;
+  int32_t pad;
+};
+
+struct RigDev {
+  int32_t n_cams;
+  int32_t flags;
+  CamDev cam[M3D_MAXC];
+};
+
+M3D_HD double qnan() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return NAN;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// undistortion: pixel -> normalised coordinates
+// ---------------------------------------------------------------------------------------
+
+// cv2.undistortPoints(pts, K, dist): x0 = (u-cx)/fx; exactly 5 iterations of the
+// fixed-point update, bail-out to (x0, y0) when icdist < 0 (OpenCV
+// cvUndistortPointsInternal, TermCriteria(MAX_ITER, 5)).  FULL = rational (k4..k6) and
+// thin-prism (s1..s4) terms present.
+template <bool FULL>
+M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double x0 = (u - c.cx) * c.ifx;
+  const double y0 = (v - c.cy) * c.ify;
+  double x = x0, y = y0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    double icdist;
+    if (FULL) {
+      icdist = (1.0 + ((c.k[7] * r2 + c.k[6]) * r2 + c.k[5]) * r2) /
+               (1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
+    } else {
+      icdist = 1.0 / (1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
+    }
+    if (icdist < 0.0) {
+      x = x0;
+      y = y0;
+      break;
+    }
+    double dx = 2.0 * c.k[2] * x * y + c.k[3] * (r2 + 2.0 * x * x);
+    double dy = c.k[2] * (r2 + 2.0 * y * y) + 2.0 * c.k[3] * x * y;
+    if (FULL) {
+      dx += c.k[8] * r2 + c.k[9] * r2 * r2;
+      dy += c.k[10] * r2 + c.k[11] * r2 * r2;
+    }
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  xo = x;
+  yo = y;
+}
+
+// cv2.fisheye.undistortPoints(pts, K, D): Newton on theta, <= 10 iterations, stop when
+// |fix| < 1e-8; non-converged or sign-flipped -> (-1e6, -1e6) (OpenCV >= 4.5).
+M3D_HD void undistort_fisheye(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double pw1 = (v - c.cy) / c.fy;
+  double pw0 = (u - c.cx) / c.fx;
+  const double alpha = c.skew / c.fx;
+  if (alpha != 0.0) pw0 -= alpha * pw1;
+  const double half_pi = 1.5707963267948966;
+  double theta_d = sqrt(pw0 * pw0 + pw1 * pw1);
+  // std::min(std::max(-pi/2, theta_d), pi/2): NaN collapses to -pi/2
+  theta_d = (-half_pi < theta_d) ? theta_d : -half_pi;
+  theta_d = (theta_d < half_pi) ? theta_d : half_pi;
+  bool converged = false;
+  double theta = theta_d, scale = 0.0;
+  if (fabs(theta_d) > 1e-8) {
+    for (int j = 0; j < 10; ++j) {
+      const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+      const double k0 = c.k[0] * t2, k1 = c.k[1] * t4, k2 = c.k[2] * t6, k3 = c.k[3] * t8;
+      const double fix = (theta * (1.0 + k0 + k1 + k2 + k3) - theta_d) /
+                         (1.0 + 3.0 * k0 + 5.0 * k1 + 7.0 * k2 + 9.0 * k3);
+      theta -= fix;
+      if (fabs(fix) < 1e-8) {
+        converged = true;
+        break;
+      }
+    }
+    scale = tan(theta) / theta_d;
+  } else {
+    converged = true;
+  }
+  const bool flipped = (theta_d < 0.0 && theta > 0.0) || (theta_d > 0.0 && theta < 0.0);
+  if (converged && !flipped) {
+    xo = pw0 * scale;
+    yo = pw1 * scale;
+  } else {
+    xo = -1000000.0;
+    yo = -1000000.0;
+  }
+}
+
+// cv2.omnidir.undistortPoints(pts, K, D, xi, R = I) (Mei model; restated from the
+// published opencv_contrib ccalib algorithm, parity unpinned).
+M3D_HD void undistort_omnidir(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double k1 = c.k[0], k2 = c.k[1], p1 = c.k[2], p2 = c.k[3], xi = c.xi;
+  const double ppx = (u * c.fy - c.cx * c.fy - c.skew * (v - c.cy)) / (c.fx * c.fy);
+  const double ppy = (v - c.cy) / c.fy;
+  double pux = ppx, puy = ppy;
+  for (int j = 0; j < 20; ++j) {
+    const double r2 = pux * pux + puy * puy;
+    const double r4 = r2 * r2;
+    const double den = 1.0 + k1 * r2 + k2 * r4;
+    pux = (ppx - 2.0 * p1 * pux * puy - p2 * (r2 + 2.0 * pux * pux)) / den;
+    puy = (ppy - 2.0 * p2 * pux * puy - p1 * (r2 + 2.0 * puy * puy)) / den;
+  }
+  const double r2 = pux * pux + puy * puy;
+  const double a = r2 + 1.0;
+  const double b = 2.0 * xi * r2;
+  const double cc = r2 * xi * xi - 1.0;
+  const double Zs = (-b + sqrt(b * b - 4.0 * a * cc)) / (2.0 * a);
+  const double X0 = pux * (Zs + xi), X1 = puy * (Zs + xi), X2 = Zs;
+  const double nrm = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
+  const double s0 = X0 / nrm, s1 = X1 / nrm, s2 = X2 / nrm;
+  xo = s0 / s2;
+  yo = s1 / s2;
+}
+
+template <bool FULL, bool PINHOLE_ONLY>
+M3D_HD void undistort_point(const CamDev& c, double u, double v, double& x, double& y) {
+  if (PINHOLE_ONLY || c.model == PINHOLE) {
+    undistort_pinhole<FULL>(c, u, v, x, y);
+  } else if (c.model == FISHEYE) {
+    undistort_fisheye(c, u, v, x, y);
+  } else {
+    undistort_omnidir(c, u, v, x, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// projection: 3D world point -> pixel
+// ---------------------------------------------------------------------------------------
+
+M3D_HD void to_camera(const CamDev& c, double X, double Y, double Z, double& xc, double& yc,
+                      double& zc) {
+  xc = c.R[0] * X + c.R[1] * Y + c.R[2] * Z + c.t[0];
+  yc = c.R[3] * X + c.R[4] * Y + c.R[5] * Z + c.t[1];
+  zc = c.R[6] * X + c.R[7] * Y + c.R[8] * Z + c.t[2];
+}
+
+// normalised (x, y) -> pixel with the pinhole distortion model (second half of
+// cv2.projectPoints)
+template <bool FULL>
+M3D_HD void distort_pinhole(const CamDev& c, double x, double y, double& u, double& v) {
+  const double r2 = x * x + y * y;
+  const double r4 = r2 * r2;
+  const double r6 = r4 * r2;
+  const double a1 = 2.0 * x * y;
+  const double a2 = r2 + 2.0 * x * x;
+  const double a3 = r2 + 2.0 * y * y;
+  double cdist = 1.0 + c.k[0] * r2 + c.k[1] * r4 + c.k[4] * r6;
+  double xd, yd;
+  if (FULL) {
+    const double icdist2 = 1.0 / (1.0 + c.k[5] * r2 + c.k[6] * r4 + c.k[7] * r6);
+    xd = x * cdist * icdist2 + c.k[2] * a1 + c.k[3] * a2 + c.k[8] * r2 + c.k[9] * r4;
+    yd = y * cdist * icdist2 + c.k[2] * a3 + c.k[3] * a1 + c.k[10] * r2 + c.k[11] * r4;
+  } else {
+    xd = x * cdist + c.k[2] * a1 + c.k[3] * a2;
+    yd = y * cdist + c.k[2] * a3 + c.k[3] * a1;
+  }
+  u = xd * c.fx + c.cx;
+  v = yd * c.fy + c.cy;
+}
+
+// cv2.projectPoints: 1/z with z == 0 -> 1; points behind the camera are not rejected.
+template <bool FULL>
+M3D_HD void project_pinhole(const CamDev& c, double X, double Y, double Z, double& u, double& v) {
+  double xc, yc, zc;
+  to_camera(c, X, Y, Z, xc, yc, zc);
+  const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
+  distort_pinhole<FULL>(c, xc * iz, yc * iz, u, v);
+}
+
+M3D_HD void distort_fisheye_cam(const CamDev& c, double xc, double yc, double zc, double& u,
+                                double& v) {
+  const double x = xc / zc, y = yc / zc;
+  const double r2 = x * x + y * y;
+  const double r = sqrt(r2);
+  const double theta = atan(r);
+  const double t2 = theta * theta, t3 = t2 * theta, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+  const double theta_d = theta + c.k[0] * t3 + c.k[1] * t5 + c.k[2] * t7 + c.k[3] * t9;
+  const double inv_r = r > 1e-8 ? 1.0 / r : 1.0;
+  double cdist = r > 1e-8 ? theta_d * inv_r : 1.0;
+  if (r != r) cdist = r;  // NaN propagates
+  const double xd1 = x * cdist, xd2 = y * cdist;
+  const double alpha = c.skew / c.fx;
+  u = c.fx * (xd1 + alpha * xd2) + c.cx;
+  v = c.fy * xd2 + c.cy;
+}
+
+M3D_HD void distort_omnidir_cam(const CamDev& c, double xc, double yc, double zc, double& u,
+                                double& v) {
+  const double k1 = c.k[0], k2 = c.k[1], p1 = c.k[2], p2 = c.k[3];
+  const double nrm = sqrt(xc * xc + yc * yc + zc * zc);
+  const double s0 = xc / nrm, s1 = yc / nrm, s2 = zc / nrm;
+  const double xu = s0 / (s2 + c.xi), yu = s1 / (s2 + c.xi);
+  const double r2 = xu * xu + yu * yu, r4 = r2 * r2;
+  const double rad = 1.0 + k1 * r2 + k2 * r4;
+  const double xd = xu * rad + 2.0 * p1 * xu * yu + p2 * (r2 + 2.0 * xu * xu);
+  const double yd = yu * rad + p1 * (r2 + 2.0 * yu * yu) + 2.0 * p2 * xu * yu;
+  u = c.fx * xd + c.skew * yd + c.cx;
+  v = c.fy * yd + c.cy;
+}
+
+template <bool FULL, bool PINHOLE_ONLY>
+M3D_HD void project_point(const CamDev& c, double X, double Y, double Z, double& u, double& v) {
+  if (PINHOLE_ONLY || c.model == PINHOLE) {
+    project_pinhole<FULL>(c, X, Y, Z, u, v);
+  } else {
+    double xc, yc, zc;
+    to_camera(c, X, Y, Z, xc, yc, zc);
+    if (c.model == FISHEYE) {
+      distort_fisheye_cam(c, xc, yc, zc, u, v);
+    } else {
+      distort_omnidir_cam(c, xc, yc, zc, u, v);
+    }
+  }
+}
+
+// Camera.distort_points: projectPoints of (x, y, 1) with identity extrinsics.
+template <bool FULL>
+M3D_HD void distort_point(const CamDev& c, double x, double y, double& u, double& v) {
+  if (c.model == PINHOLE) {
+    distort_pinhole<FULL>(c, x, y, u, v);
+  } else if (c.model == FISHEYE) {
+    distort_fisheye_cam(c, x, y, 1.0, u, v);
+  } else {
+    distort_omnidir_cam(c, x, y, 1.0, u, v);
+  }
+}
+
+// residual norm exactly as np.linalg.norm(axis=2): sqrt(ex*ex + ey*ey)
+M3D_HD double residual_norm(double ex, double ey) { return sqrt(ex * ex + ey * ey); }
+
+// ---------------------------------------------------------------------------------------
+// DLT normal equations.  For camera rows a1 = x*M[2]-M[0], a2 = y*M[2]-M[1] (M = [R|t])
+// the 4x4 Gram matrix G = sum a a^T is kept in block form
+//   G = [ H  g ]   H: 3x3 symmetric (h[0..5] = xx xy xz yy yz zz), g: 3-vector, w: scalar
+//       [ g' w ]
+// ---------------------------------------------------------------------------------------
+struct Gram {
+  double h[6];
+  double g[3];
+  double w;
+};
+
+M3D_HD void gram_zero(Gram& G) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) G.h[i] = 0.0;
+  G.g[0] = G.g[1] = G.g[2] = 0.0;
+  G.w = 0.0;
+}
+
+M3D_HD void gram_add_row(Gram& G, double a0, double a1, double a2, double a3) {
+  G.h[0] += a0 * a0;
+  G.h[1] += a0 * a1;
+  G.h[2] += a0 * a2;
+  G.h[3] += a1 * a1;
+  G.h[4] += a1 * a2;
+  G.h[5] += a2 * a2;
+  G.g[0] += a0 * a3;
+  G.g[1] += a1 * a3;
+  G.g[2] += a2 * a3;
+  G.w += a3 * a3;
+}
+
+// rows of camera c for the undistorted observation (x, y)   (cameras.py:27-28)
+M3D_HD void gram_add_camera(Gram& G, const CamDev& c, double x, double y) {
+  gram_add_row(G, x * c.R[6] - c.R[0], x * c.R[7] - c.R[1], x * c.R[8] - c.R[2],
+               x * c.t[2] - c.t[0]);
+  gram_add_row(G, y * c.R[6] - c.R[3], y * c.R[7] - c.R[4], y * c.R[8] - c.R[5],
+               y * c.t[2] - c.t[1]);
+}
+
+M3D_HD void gram_add(Gram& G, const Gram& B) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) G.h[i] += B.h[i];
+  G.g[0] += B.g[0];
+  G.g[1] += B.g[1];
+  G.g[2] += B.g[2];
+  G.w += B.w;
+}
+
+// Fallback eigen-solver: cyclic Jacobi on the full 4x4 Gram matrix, returns the
+// eigenvector of the smallest eigenvalue dehomogenised.  Only reached for degenerate
+// geometry (H singular, point at infinity, lambda_1 not separated).
+M3D_HD_NOINLINE void dlt_solve_jacobi(const Gram& G, double& X, double& Y, double& Z) {
+  double A[4][4] = {{G.h[0], G.h[1], G.h[2], G.g[0]},
+                    {G.h[1], G.h[3], G.h[4], G.g[1]},
+                    {G.h[2], G.h[4], G.h[5], G.g[2]},
+                    {G.g[0], G.g[1], G.g[2], G.w}};
+  double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      diag += A[i][i] * A[i][i];
+      for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
+    }
+    if (!(off > 1e-60 * diag)) break;
+    for (int p = 0; p < 3; ++p) {
+      for (int q = p + 1; q < 4; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int r = 0; r < 4; ++r) {
+          const double arp = A[r][p], arq = A[r][q];
+          A[r][p] = cs * arp - sn * arq;
+          A[r][q] = sn * arp + cs * arq;
+        }
+        for (int r = 0; r < 4; ++r) {
+          const double apr = A[p][r], aqr = A[q][r];
+          A[p][r] = cs * apr - sn * aqr;
+          A[q][r] = sn * apr + cs * aqr;
+        }
+        for (int r = 0; r < 4; ++r) {
+          const double vrp = V[r][p], vrq = V[r][q];
+          V[r][p] = cs * vrp - sn * vrq;
+          V[r][q] = sn * vrp + cs * vrq;
+        }
+      }
+    }
+  }
+  int m = 0;
+  for (int i = 1; i < 4; ++i)
+    if (A[i][i] < A[m][m]) m = i;
+  X = V[0][m] / V[3][m];
+  Y = V[1][m] / V[3][m];
+  Z = V[2][m] / V[3][m];
+}
+
+// Smallest eigenvector of G, dehomogenised (= vh[-1][:3]/vh[-1][3] of the SVD of the DLT
+// matrix, cameras.py:29-31).  With v = (X, 1) the eigen-equations are
+//   (H - lam I) X = -g ,   f(lam) := w - lam + g.X(lam) = 0 ,
+// f is concave and decreasing on [0, lam_min(H)), and its only root there is lam_min(G)
+// (Cauchy interlacing).  Newton on f from lam = 0 is Rayleigh-quotient iteration in this
+// block form: lam += f / (1 + |X|^2).  The 3x3 systems are solved with the adjugate;
+// H (entries O(k)) is well conditioned, the O(|t|^2) dynamic range of G stays in g and w,
+// which is why this is more accurate than an eigen-decomposition of G itself
+// (measured: <= 2e-11 px in mean reprojection error vs extended precision; LAPACK's SVD
+// of the DLT matrix: ~1e-10 px).
+M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
+  double lam = 0.0;
+  double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+  bool ok = false;
+  const double tr = G.h[0] + G.h[3] + G.h[5];
+#pragma unroll 1
+  for (int it = 0; it < 12; ++it) {
+    const double a = G.h[0] - lam, b = G.h[1], c = G.h[2], d = G.h[3] - lam, e = G.h[4],
+                 f = G.h[5] - lam;
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+    const double det = a * c00 + b * c01 + c * c02;
+    // positive definite (Sylvester) <=> lam < lam_min(H): we are on the right branch
+    if (!(a > 0.0 && c22 > 0.0 && det > 0.0)) break;
+    const double idet = 1.0 / det;
+    x0 = -(c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2]) * idet;
+    x1 = -(c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2]) * idet;
+    x2 = -(c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2]) * idet;
+    const double fl = G.w - lam + (G.g[0] * x0 + G.g[1] * x1 + G.g[2] * x2);
+    const double n2 = 1.0 + x0 * x0 + x1 * x1 + x2 * x2;
+    const double dl = fl / n2;
+    // lam_min(H - lam I) >= det / tr^2 ; a step below 1e-7 of that changes X by < 1e-14 |X|
+    // beyond the first-order correction applied here.
+    const double mu_lb = det / (tr * tr);
+    if (fabs(dl) <= 1e-7 * mu_lb) {
+      // first-order update X(lam + dl) = X + dl (H - lam I)^-1 X
+      const double y0 = (c00 * x0 + c01 * x1 + c02 * x2) * idet;
+      const double y1 = (c01 * x0 + c11 * x1 + c12 * x2) * idet;
+      const double y2 = (c02 * x0 + c12 * x1 + c22 * x2) * idet;
+      x0 += dl * y0;
+      x1 += dl * y1;
+      x2 += dl * y2;
+      ok = true;
+      break;
+    }
+    lam += dl;
+    if (!(lam >= 0.0)) break;  // also catches NaN
+  }
+  if (ok) {
+    X = x0;
+    Y = x1;
+    Z = x2;
+  } else {
+    dlt_solve_jacobi(G, X, Y, Z);
+  }
+}
+
+// Inhomogeneous least squares X = -pinv(A[:, :3]) A[:, 3] = -H^-1 g
+// (multicam_toolbox.py:476-484); rank-deficient H falls back to the pseudo-inverse
+// through the eigen-decomposition of H.
+M3D_HD void ls_solve(const Gram& G, double& X, double& Y, double& Z) {
+  const double a = G.h[0], b = G.h[1], c = G.h[2], d = G.h[3], e = G.h[4], f = G.h[5];
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double idet = 1.0 / det;
+  X = -(c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2]) * idet;
+  Y = -(c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2]) * idet;
+  Z = -(c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2]) * idet;
+}
+
+// ---------------------------------------------------------------------------------------
+// camera-subset enumeration of triangulate_possible (cameras.py:689-692)
+// ---------------------------------------------------------------------------------------
+
+// Camera mask of enumeration step s for valid-camera mask vmask (k = popcount):
+// the j-th valid camera (ascending) is included iff bit (k-1-j) of s is 0.
+M3D_HD uint32_t subset_mask(uint32_t vmask, int k, uint32_t s) {
+  uint32_t m = 0;
+  int j = 0;
+  for (uint32_t rest = vmask; rest; rest &= rest - 1, ++j) {
+    const uint32_t low = rest & (0u - rest);
+    if (!((s >> (k - 1 - j)) & 1u)) m |= low;
+  }
+  return m;
+}
+
+}  // namespace m3d

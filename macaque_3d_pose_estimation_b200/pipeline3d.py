@@ -1,0 +1,56 @@
+"""The 3D stage of the reference pipeline (src/pipeline/step4_aniposefiltering.py:219-339)
+on the GPU CameraGroup: score gating -> triangulate / triangulate_ransac ->
+reprojection error -> per-joint score and error arrays.
+
+All animals are reconstructed in ONE kernel call (the reference loops over animals and
+points in Python, step4:219, cameras.py:628/683); file I/O, calibration assembly and the
+Viterbi filter around it are unchanged reference territory and not reimplemented here.
+The ``optim=True`` branch (CameraGroup.optim_points, step4:228-291) is outside the
+accelerated path.
+"""
+import numpy as np
+
+
+def reconstruct(cgroup, kp2d_f, score_threshold=0.5, ransac=False, optim=False, min_cams=3):
+    """kp2d_f: (A, C, F, J, 3) float64 [x, y, score] — the array step4 holds after
+    ``kp2d_f.transpose((2,4,0,1,3))`` (step4:190).  Like the reference, keypoints whose
+    score is below the threshold are set to NaN IN PLACE and the scores of unused views are
+    overwritten with 2 (step4:225-226, 287, 314).
+
+    Returns {'kp3d': (A,F,J,3), 'kp3d_score': (A,F,J), 'kp3d_err': (A,F,J), 'num_cams': (A,F,J)}.
+    ``min_cams`` is the value step4 passes to triangulate_ransac (:297).
+    """
+    if optim:
+        raise NotImplementedError(
+            "optim=True (CameraGroup.optim_points, step4_aniposefiltering.py:247-271) is outside "
+            "the accelerated hot path; run with config['triangulation']['optim'] = false")
+    n_animal, n_cam, n_frame, n_kp, _ = kp2d_f.shape
+    assert n_cam == len(cgroup.cameras), \
+        "kp2d_f has {} cameras, camera group has {}".format(n_cam, len(cgroup.cameras))
+    all_points_raw = kp2d_f[..., :2]
+    all_scores = kp2d_f[..., 2]
+    bad = all_scores < score_threshold                                   # step4:225-226
+    all_points_raw[bad] = np.nan
+
+    # (A, C, F, J, 2) -> (C, A*F*J, 2): one launch for every animal
+    pts = np.ascontiguousarray(all_points_raw.transpose(1, 0, 2, 3, 4)).reshape(n_cam, -1, 2)
+    if ransac:
+        p3d, picked, p2ds, errors = cgroup.triangulate_ransac(pts, min_cams=min_cams)   # step4:296-297
+        picked_shaped = p2ds.reshape(n_cam, n_animal, n_frame, n_kp, 2)
+        good = ~np.isnan(picked_shaped[..., 0])                           # step4:299-300
+        num_cams = picked.sum(axis=0).sum(axis=1).reshape(n_animal, n_frame, n_kp).astype('float')
+    else:
+        p3d, errors = cgroup.triangulate_with_error(pts)                  # step4:306-307 fused
+        good = ~np.isnan(pts.reshape(n_cam, n_animal, n_frame, n_kp, 2)[..., 0])
+        num_cams = good.sum(axis=0).astype('float')                      # step4:308-309
+    kp3d = p3d.reshape(n_animal, n_frame, n_kp, 3)
+    E = errors.reshape(n_animal, n_frame, n_kp).copy()
+
+    good_a = good.transpose(1, 0, 2, 3)                                  # (A, C, F, J)
+    all_scores[~good_a] = 2                                              # step4:314
+    S = np.min(all_scores, axis=1)                                       # step4:315
+    few = num_cams < 2
+    S[few] = np.nan                                                      # step4:317-319
+    E[few] = np.nan
+    num_cams[few] = np.nan
+    return {'kp3d': kp3d, 'kp3d_score': S, 'kp3d_err': E, 'num_cams': num_cams}

@@ -1,0 +1,113 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/m3d.h declares, and the
+product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from macaque_3d_pose_estimation_b200 import _lib, synth
+from macaque_3d_pose_estimation_b200.cameras import Camera, CameraGroup, FisheyeCamera, OmnidirCamera
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "m3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(m3d_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libm3d.so does not export " + n
+        assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
+
+
+def test_struct_layout_matches_header():
+    # struct m3d_cam: 2 x int32 + (9 + 14 + 3 + 3 + 1) doubles
+    assert ctypes.sizeof(_lib.M3DCam) == 8 + 8 * 30
+
+
+def test_version_and_errors(lib):
+    assert lib.m3d_version() >= 100
+    h = ctypes.c_void_p()
+    assert lib.m3d_rig_create(None, 1, 0, ctypes.byref(h)) != 0
+    assert _lib.last_error() != ""
+
+
+def _no_gpu(lib):
+    return lib.m3d_device_count() <= 0
+
+
+def test_fails_loudly_without_gpu(lib):
+    if not _no_gpu(lib):
+        pytest.skip("a GPU is visible")
+    cg = CameraGroup.from_dicts(synth.make_rig(8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cg.triangulate(np.zeros((8, 4, 2)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cg.cameras[0].undistort_points(np.zeros((4, 2)))
+
+
+def test_host_side_api_mirrors_reference():
+    dicts = synth.make_rig(8, "pinhole")
+    cg = CameraGroup.from_dicts(dicts)
+    assert cg.get_names() == [str(i + 1) for i in range(8)]
+    sub = cg.subset_cameras_names(["3", "1"])
+    assert sub.get_names() == ["3", "1"]
+    assert sub.cameras[0] is not cg.cameras[2]                 # deep copies (cameras.py:564)
+    with pytest.raises(IndexError, match="not part of camera names"):
+        cg.subset_cameras_names(["99"])
+    with pytest.raises(AssertionError, match="first dim should be equal to number of cameras"):
+        cg.triangulate(np.zeros((7, 4, 2)))
+    with pytest.raises(AssertionError, match="first dim should be equal to number of cameras"):
+        cg.triangulate_ransac(np.zeros((3, 4, 2)))
+    with pytest.raises(AssertionError, match="not consistent"):
+        cg.reprojection_error(np.zeros((5, 3)), np.zeros((8, 4, 2)))
+    with pytest.raises(NotImplementedError, match="1116"):
+        cg.optim_points()
+    d = cg.cameras[0].get_dict()
+    assert set(d) == {"name", "size", "matrix", "distortions", "rotation", "translation"}
+    cam = Camera.from_dict(d)
+    assert np.array_equal(cam.get_camera_matrix(), cg.cameras[0].get_camera_matrix())
+    p = cam.get_params()
+    cam.set_params(p)
+    assert cam.get_distortions().shape == (5,)
+    f = FisheyeCamera(name="f", size=(640, 480))
+    assert f.get_dict()["fisheye"] is True and f.get_distortions().shape == (4,)
+    o = OmnidirCamera(name="o", size=(640, 480), xi=[1.2], K=np.eye(3), D=np.zeros(4))
+    assert "Omnidir" in o.get_dict() and o.copy().get_xi()[0] == 1.2
+    cgf = CameraGroup.from_dicts([f.get_dict(), dict(o.get_dict(), omnidir=True)])
+    assert isinstance(cgf.cameras[0], FisheyeCamera) and isinstance(cgf.cameras[1], OmnidirCamera)
+
+
+def test_dump_load_roundtrip(tmp_path):
+    cg = CameraGroup.from_dicts(synth.make_rig(4, "pinhole"))
+    cg.metadata = {"error": 0.24}
+    fn = str(tmp_path / "calibration.toml")
+    cg.dump(fn)
+    cg2 = CameraGroup.load(fn)
+    assert cg2.get_names() == cg.get_names()
+    assert cg2.metadata["error"] == 0.24
+    for a, b in zip(cg.cameras, cg2.cameras):
+        assert np.allclose(a.get_camera_matrix(), b.get_camera_matrix(), rtol=0, atol=0)
+        assert np.array_equal(a.get_rotation(), b.get_rotation())
+
+
+def test_rig_rejects_bad_parameters(lib):
+    if _no_gpu(lib):
+        pytest.skip("rig validation needs the device check to pass first")
+    cam = Camera(dist=np.zeros(7), name="bad")
+    with pytest.raises(RuntimeError, match="4, 5, 8, 12 or 14"):
+        CameraGroup([cam]).project(np.zeros((1, 3)))

@@ -1,0 +1,258 @@
+"""GPU tier: the CUDA path, called through the C-ABI (libm3d.so) via the drop-in Python
+classes, against (1) the golden vectors produced by the unmodified reference, (2) the
+oracle on seeded random inputs, (3) size-independent properties at larger N.
+
+Tolerances (BASELINE.json north_star): selected camera subsets and inlier masks bit-exact;
+3D points within 1e-4 relative or 0.01 mm (asserted: 1e-6 mm); reprojection errors within
+1e-3 px (asserted: 1e-7 px)."""
+import numpy as np
+import pytest
+
+from macaque_3d_pose_estimation_b200 import _lib, synth
+from macaque_3d_pose_estimation_b200.cameras import Camera, CameraGroup, FisheyeCamera, OmnidirCamera
+from oracle import cameragroup as og
+from oracle import fixtures
+
+pytestmark = pytest.mark.gpu
+
+DLT = fixtures.golden_names("dlt")
+RANSAC = fixtures.golden_names("ransac")
+P3D_TOL_MM = 1e-6
+ERR_TOL_PX = 1e-7
+
+
+def group_from_golden(g):
+    cams = []
+    for i in range(g["rig_model"].shape[0]):
+        n = int(g["rig_ndist"][i])
+        kw = dict(size=(2048, 1536), rvec=g["rig_rvec"][i], tvec=g["rig_tvec"][i], name=str(g["rig_names"][i]))
+        m = int(g["rig_model"][i])
+        if m == 0:
+            cams.append(Camera(matrix=g["rig_K"][i], dist=g["rig_dist"][i, :n], **kw))
+        elif m == 1:
+            cams.append(FisheyeCamera(matrix=g["rig_K"][i], dist=g["rig_dist"][i, :n], **kw))
+        else:
+            cams.append(OmnidirCamera(K=g["rig_K"][i], D=g["rig_dist"][i, :n], xi=[g["rig_xi"][i]], **kw))
+    return CameraGroup(cams)
+
+
+def _eq_nan(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as ge
+    ge.build()
+    assert _lib.load().m3d_device_count() > 0
+
+
+@pytest.mark.parametrize("name", DLT)
+def test_gpu_dlt_golden(name):
+    import torch
+    g, _ = fixtures.load_golden(name)
+    cg = group_from_golden(g)
+    before = _lib.load().m3d_launch_count()
+    # per-camera Camera.undistort_points and the batched group form
+    und = np.stack([cam.undistort_points(np.copy(g["p2d"][c])) for c, cam in enumerate(cg.cameras)])
+    assert _eq_nan(und, g["undistorted"])
+    assert np.nanmax(np.abs(und - g["undistorted"])) <= 1e-12
+    und2 = cg.undistort_points(g["p2d"])
+    assert np.array_equal(und, und2, equal_nan=True)
+    # triangulate (host-buffer pipeline) and the device-resident torch path
+    p3d = cg.triangulate(g["p2d"])
+    assert p3d.shape == g["p3d"].shape and p3d.dtype == np.float64
+    assert _eq_nan(p3d, g["p3d"])
+    assert np.nanmax(np.abs(p3d - g["p3d"])) <= P3D_TOL_MM
+    p3d_t = cg.triangulate(torch.from_numpy(g["p2d"]).cuda())
+    assert p3d_t.is_cuda and np.array_equal(p3d_t.cpu().numpy(), p3d, equal_nan=True)
+    p3d_nu = cg.triangulate(g["undistorted"], undistort=False)
+    assert np.nanmax(np.abs(p3d_nu - g["p3d_noundist"])) <= P3D_TOL_MM
+    # reprojection error, both forms, evaluated at the REFERENCE's 3D points
+    ef = cg.reprojection_error(g["p3d"], g["p2d"])
+    assert ef.shape == g["err_full"].shape and _eq_nan(ef, g["err_full"])
+    assert np.nanmax(np.abs(ef - g["err_full"])) <= 1e-9
+    em = cg.reprojection_error(g["p3d"], g["p2d"], mean=True)
+    assert em.shape == g["err_mean"].shape and _eq_nan(em, g["err_mean"])
+    assert np.nanmax(np.abs(em - g["err_mean"])) <= 1e-9
+    # fused kernel: error at OUR 3D points
+    p3f, emf = cg.triangulate_with_error(g["p2d"])
+    assert np.array_equal(p3f, p3d, equal_nan=True)
+    assert _eq_nan(emf, g["err_mean"]) and np.nanmax(np.abs(emf - g["err_mean"])) <= ERR_TOL_PX
+    # projection
+    proj = cg.project(g["X_true"])
+    assert proj.shape == g["proj_true"].shape
+    assert np.abs(proj - g["proj_true"]).max() <= 1e-9
+    pc = cg.cameras[0].project(g["X_true"])
+    assert pc.shape == (g["X_true"].shape[0], 1, 2)
+    assert np.abs(pc.reshape(-1, 2) - g["proj_true"][0]).max() <= 1e-9
+    # one-point overloads (cameras.py:603-606, 753-757)
+    i = int(np.nonzero(np.isfinite(g["p3d"][:, 0]))[0][0])
+    one = cg.triangulate(g["p2d"][:, i])
+    assert one.shape == (3,) and np.abs(one - g["p3d"][i]).max() <= P3D_TOL_MM
+    e1 = cg.reprojection_error(g["p3d"][i], g["p2d"][:, i], mean=True)
+    assert isinstance(e1, float) and abs(e1 - g["err_mean"][i]) <= 1e-9
+    e2 = cg.reprojection_error(g["p3d"][i], g["p2d"][:, i])
+    assert e2.shape == (len(cg.cameras), 2)
+    assert np.abs(cg.get_extrinsics_mats() - np.array([c.extrinsics() for c in fixtures.cams_from_arrays(g)])).max() == 0
+    assert _lib.load().m3d_launch_count() > before          # the CUDA kernels really ran
+
+
+@pytest.mark.parametrize("name", RANSAC)
+def test_gpu_ransac_golden(name):
+    import torch
+    g, _ = fixtures.load_golden(name)
+    cg = group_from_golden(g)
+    mc = int(g["min_cams"])
+    out, picked, p2d, err, sidx, nev = cg.triangulate_ransac(np.copy(g["p2d"]), min_cams=mc, return_stats=True)
+    assert picked.dtype == np.bool_ and picked.shape == g["picked"].shape
+    assert np.array_equal(picked, g["picked"])                     # bit-exact inlier masks
+    assert np.array_equal(p2d, g["points_2d"], equal_nan=True)
+    assert _eq_nan(out, g["p3d"])
+    assert np.nanmax(np.abs(out - g["p3d"]), initial=0.0) <= P3D_TOL_MM
+    assert np.abs(err - g["errors"]).max() <= ERR_TOL_PX
+    assert int(nev.sum()) == int(g["n_subsets_evaluated"])         # identical search length
+    # device-resident path returns the same bits
+    t = cg.triangulate_ransac(torch.from_numpy(g["p2d"]).cuda(), min_cams=mc, return_stats=True)
+    assert np.array_equal(t[1].cpu().numpy(), picked)
+    assert np.array_equal(t[0].cpu().numpy(), out, equal_nan=True)
+    assert np.array_equal(t[3].cpu().numpy(), err)
+    assert np.array_equal(t[4].cpu().numpy(), sidx)
+    # triangulate_possible with P = 1 is the same search (cameras.py:738-743)
+    tp = cg.triangulate_possible(g["p2d"].reshape(g["p2d"].shape[0], -1, 1, 2), min_cams=mc)
+    assert np.array_equal(tp[1], picked) and np.array_equal(tp[0], out, equal_nan=True)
+
+
+@pytest.mark.parametrize("n_cams,model,kw", [
+    (8, "pinhole", dict(p_outlier=0.2, p_missing=0.1)),
+    (8, "pinhole", dict(noise=2.0, p_outlier=0.4, p_missing=0.1)),
+    (8, "pinhole8", dict(p_outlier=0.2, p_missing=0.2)),
+    (8, "fisheye", dict(p_outlier=0.2, p_missing=0.1)),
+    (8, "omnidir", dict(p_outlier=0.2, p_missing=0.1)),
+    (5, "pinhole", dict(p_outlier=0.3, p_missing=0.1)),
+    (2, "pinhole", dict(p_outlier=0.1, p_missing=0.1)),
+    (11, "pinhole", dict(p_outlier=0.1, p_missing=0.1)),
+])
+def test_gpu_ransac_random_vs_oracle(n_cams, model, kw):
+    seed = 777 + n_cams
+    dicts = synth.make_rig(n_cams, model, seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    n_frames = 8 if n_cams > 8 else 60
+    X = synth.make_tracks(n_frames, 4, seed=seed).reshape(-1, 3)
+    p2 = synth.corrupt(og.project(cams, X), seed=seed, **kw)
+    for mc in (2, 3):
+        o = og.triangulate_ransac(cams, p2, min_cams=mc, return_stats=True)
+        h = cg.triangulate_ransac(p2, min_cams=mc, return_stats=True)
+        assert np.array_equal(o[1], h[1])
+        assert np.array_equal(o[4], h[4])
+        assert np.array_equal(o[5], h[5])
+        assert np.array_equal(o[2], h[2], equal_nan=True)
+        assert np.nanmax(np.abs(o[0] - h[0]), initial=0.0) <= P3D_TOL_MM
+        assert np.abs(o[3] - h[3]).max() <= ERR_TOL_PX
+
+
+def test_gpu_empty_and_ragged_inputs():
+    cg = CameraGroup.from_dicts(synth.make_rig(8, "pinhole", seed=3))
+    z = np.zeros((8, 0, 2))
+    assert cg.triangulate(z).shape == (0, 3)
+    r = cg.triangulate_ransac(z)
+    assert r[0].shape == (0, 3) and r[1].shape == (8, 0, 1) and r[2].shape == (8, 0, 2) and r[3].shape == (0,)
+    assert cg.reprojection_error(np.zeros((0, 3)), z, mean=True).shape == (0,)
+    assert cg.project(np.zeros((0, 3))).shape == (8, 0, 2)
+    # all-NaN input: nothing triangulated, errors default to 0.0 for RANSAC, NaN for the mean
+    nan = np.full((8, 37, 2), np.nan)
+    assert np.isnan(cg.triangulate(nan)).all()
+    out, picked, p2, err = cg.triangulate_ransac(nan)
+    assert np.isnan(out).all() and not picked.any() and np.isnan(p2).all() and (err == 0.0).all()
+    # N not a multiple of the warp / block size, and a 1-camera group
+    cams = fixtures.cams_from_dicts(synth.make_rig(8, "pinhole", seed=3))
+    X = synth.make_tracks(3, 1, seed=3).reshape(-1, 3)[:33]
+    p2 = og.project(cams, X)
+    assert np.nanmax(np.abs(cg.triangulate(p2) - og.triangulate(cams, p2))) <= P3D_TOL_MM
+    one = cg.subset_cameras([2])
+    assert np.isnan(one.triangulate(p2[2:3])).all()
+
+
+def test_gpu_large_n_properties():
+    """BASELINE config-2 shaped run (8 views, ~1e6 joint-instances on the GPU) checked
+    through size-independent properties: agreement with the oracle on a random sample,
+    chunk invariance of the host pipeline, permutation equivariance, and device == host."""
+    import torch
+    seed = 99
+    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    X = synth.make_tracks(15000, 4, seed=seed).reshape(-1, 3)          # 1.02e6 points
+    clean = cg.project(X)
+    p2 = synth.corrupt(clean, seed=seed, p_outlier=0.2, p_missing=0.1)
+    n = p2.shape[1]
+    p3d, err = cg.triangulate_with_error(p2)
+    rng = np.random.default_rng(1)
+    idx = rng.choice(n, 4000, replace=False)
+    ref = og.triangulate(cams, p2[:, idx])
+    assert _eq_nan(p3d[idx], ref) and np.nanmax(np.abs(p3d[idx] - ref)) <= P3D_TOL_MM
+    referr = og.reprojection_error(cams, ref, p2[:, idx], mean=True)
+    assert np.nanmax(np.abs(err[idx] - referr)) <= ERR_TOL_PX
+    # permutation equivariance + device path == host pipeline (bitwise)
+    perm = rng.permutation(n)
+    t = torch.from_numpy(np.ascontiguousarray(p2[:, perm])).cuda()
+    p3p, errp = cg.triangulate_with_error(t)
+    assert np.array_equal(p3p.cpu().numpy(), p3d[perm], equal_nan=True)
+    assert np.array_equal(errp.cpu().numpy(), err[perm], equal_nan=True)
+    # RANSAC: sample vs oracle, and equivariance
+    out, picked, _, rerr, sidx, nev = cg.triangulate_ransac(p2, return_stats=True)
+    o = og.triangulate_ransac(cams, p2[:, idx[:2000]], return_stats=True)
+    assert np.array_equal(picked[:, idx[:2000]], o[1])
+    assert np.array_equal(sidx[idx[:2000]], o[4]) and np.array_equal(nev[idx[:2000]], o[5])
+    assert np.nanmax(np.abs(out[idx[:2000]] - o[0])) <= P3D_TOL_MM
+    tr = cg.triangulate_ransac(t, return_stats=True)
+    assert np.array_equal(tr[1].cpu().numpy(), picked[:, perm])
+    assert np.array_equal(tr[0].cpu().numpy(), out[perm], equal_nan=True)
+    # selected points: reprojection error of the selection is what was reported
+    sel = sidx >= 0
+    chk = cg.reprojection_error(out, np.where(picked, p2, np.nan), mean=True)
+    assert np.nanmax(np.abs(chk[sel] - rerr[sel])) <= 1e-9
+    assert 20.0 < nev.mean() < 60.0                                   # ~1 + p (2^k - 1) subsets / point
+
+
+def test_gpu_step4_stage_matches_oracle():
+    """The 3D stage of step4_aniposefiltering.py:219-330 (plain and RANSAC branches)."""
+    from macaque_3d_pose_estimation_b200 import pipeline3d
+    seed = 5
+    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    A, F, J = 2, 40, 17
+    X = synth.make_tracks(F, A, seed=seed)                              # (F, A, J, 3)
+    p2 = synth.corrupt(og.project(cams, X.reshape(-1, 3)), seed=seed, p_outlier=0.1)
+    p2 = p2.reshape(8, F, A, J, 2).transpose(2, 0, 1, 3, 4)            # (A, C, F, J, 2)
+    rng = np.random.default_rng(seed)
+    scores = rng.uniform(0.2, 1.0, size=(A, 8, F, J))
+    kp2d = np.concatenate([p2, scores[..., None]], axis=-1)
+    for ransac in (False, True):
+        res = pipeline3d.reconstruct(cg, kp2d.copy(), score_threshold=0.5, ransac=ransac)
+        for a in range(A):
+            pts = kp2d[a, :, :, :, :2].copy()
+            sc = kp2d[a, :, :, :, 2].copy()
+            pts[sc < 0.5] = np.nan
+            flat = pts.reshape(8, F * J, 2)
+            if ransac:
+                o3, opick, o2d, oerr = og.triangulate_ransac(cams, flat, min_cams=3)
+                ncam = opick.sum(axis=0).sum(axis=1).reshape(F, J).astype(float)
+                good = ~np.isnan(o2d.reshape(8, F, J, 2)[..., 0])
+            else:
+                o3 = og.triangulate(cams, flat)
+                oerr = og.reprojection_error(cams, o3, flat, mean=True)
+                good = ~np.isnan(pts[..., 0])
+                ncam = good.sum(axis=0).astype(float)
+            sc[~good] = 2
+            s3 = sc.min(axis=0)
+            s3[ncam < 2] = np.nan
+            e3 = oerr.reshape(F, J).copy()
+            e3[ncam < 2] = np.nan
+            assert _eq_nan(res["kp3d"][a], o3.reshape(F, J, 3))
+            assert np.nanmax(np.abs(res["kp3d"][a] - o3.reshape(F, J, 3))) <= P3D_TOL_MM
+            assert np.array_equal(res["kp3d_score"][a], s3, equal_nan=True)
+            assert _eq_nan(res["kp3d_err"][a], e3)
+            assert np.nanmax(np.abs(res["kp3d_err"][a] - e3)) <= ERR_TOL_PX
