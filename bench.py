@@ -251,7 +251,8 @@ def run_gpu(args):
     C, A, J = 8, 4, 17
     F = args.frames
     seed = 20261018 + 2 + rank
-    cg = CameraGroup.from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2), device=local)
+    cg = CameraGroup.from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2))
+    cg.device = local
     X, xy = make_device_workload(cg, F, A, J, seed, args.workload, device)
     del X
     N = xy.shape[1]
@@ -349,6 +350,8 @@ def run_gpu(args):
     n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else N
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         h_xy = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True)
         h_xy.copy_(xy[:, :n_e2e])
         h_p3d = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
@@ -429,6 +432,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6 dlt, 2e5 ransac)")
     ap.add_argument("--e2e-points", type=int, default=0, help="joint-instances of the e2e run (0 = all)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.frames <= 0:
         args.frames = 1000000 if args.workload == "dlt" else 200000

@@ -14,6 +14,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -47,6 +48,7 @@ static int fail(int code, const std::string& msg) { return m3d_fail(code, msg); 
 
 struct m3d_rig {
   RigDev dev;
+  RigDev* dev_g = nullptr;  // device-resident copy (kernels that index cameras per lane)
   int device;
   // workspace of the *_host pipelines (lazily allocated, guarded by ws_mutex)
   std::mutex ws_mutex;
@@ -134,47 +136,82 @@ k_project(const __grid_constant__ RigDev rig, int cam0, int ncam, const double* 
 // ---------------------------------------------------------------------------------------
 // K2: fused undistort + DLT triangulation (+ mean reprojection error)
 // ---------------------------------------------------------------------------------------
-template <bool FULL, bool PO, bool UNDISTORT, bool WITH_ERR>
-__global__ void __launch_bounds__(256)
+// NC > 0: camera count known at compile time — the camera loops unroll completely, every
+// camera parameter becomes a constant-bank operand of the DFMA that uses it (no LDC, no
+// register), and the raw observations stay in registers for the error pass.
+// NC == 0: run-time camera count (any rig up to M3D_MAX_CAMS).
+template <bool FULL, bool PO, bool UNDISTORT, bool WITH_ERR, int NC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_triangulate(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t N,
               double* __restrict__ p3d, double* __restrict__ err) {
-  const int C = rig.n_cams;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N;
        n += (int64_t)gridDim.x * blockDim.x) {
     Gram G;
     gram_zero(G);
     int cnt = 0;
-#pragma unroll 1
-    for (int c = 0; c < C; ++c) {
-      const double2 p = ld_xy(xy, (int64_t)c * N + n);
-      double x = p.x, y = p.y;
-      if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
-      if (x == x) {  // validity on x only (cameras.py:630)
-        gram_add_camera(G, rig.cam[c], x, y);
-        ++cnt;
-      }
-    }
     double X = qnan(), Y = qnan(), Z = qnan();
-    if (cnt >= 2) dlt_solve(G, X, Y, Z);
-    p3d[3 * n] = X;
-    p3d[3 * n + 1] = Y;
-    p3d[3 * n + 2] = Z;
-    if (WITH_ERR) {
-      double sum = 0.0;
-      int m = 0;
+    if (NC > 0) {
+      double2 raw[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) raw[c] = ld_xy(xy, (int64_t)c * N + n);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double x = raw[c].x, y = raw[c].y;
+        if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], raw[c].x, raw[c].y, x, y);
+        if (x == x) {  // validity on x only (cameras.py:630)
+          gram_add_camera(G, rig.cam[c], x, y);
+          ++cnt;
+        }
+      }
+      if (cnt >= 2) dlt_solve(G, X, Y, Z);
+      if (WITH_ERR) {
+        double sum = 0.0;
+        int m = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double u, v;
+          project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
+          const double e = residual_norm(raw[c].x - u, raw[c].y - v);
+          if (e == e) {
+            sum += e;
+            ++m;
+          }
+        }
+        err[n] = (m >= 2) ? sum / (double)m : qnan();
+      }
+    } else {
+      const int C = rig.n_cams;
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
         const double2 p = ld_xy(xy, (int64_t)c * N + n);
-        double u, v;
-        project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
-        const double e = residual_norm(p.x - u, p.y - v);
-        if (e == e) {
-          sum += e;
-          ++m;
+        double x = p.x, y = p.y;
+        if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+        if (x == x) {
+          gram_add_camera(G, rig.cam[c], x, y);
+          ++cnt;
         }
       }
-      err[n] = (m >= 2) ? sum / (double)m : qnan();
+      if (cnt >= 2) dlt_solve(G, X, Y, Z);
+      if (WITH_ERR) {
+        double sum = 0.0;
+        int m = 0;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+          const double2 p = ld_xy(xy, (int64_t)c * N + n);
+          double u, v;
+          project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
+          const double e = residual_norm(p.x - u, p.y - v);
+          if (e == e) {
+            sum += e;
+            ++m;
+          }
+        }
+        err[n] = (m >= 2) ? sum / (double)m : qnan();
+      }
     }
+    p3d[3 * n] = X;
+    p3d[3 * n + 1] = Y;
+    p3d[3 * n + 2] = Z;
   }
 }
 
@@ -240,221 +277,9 @@ k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: camera-subset RANSAC (triangulate_possible with one candidate per camera)
+// K4: camera-subset RANSAC — see m3d_ransac.cuh
 // ---------------------------------------------------------------------------------------
-constexpr int RANSAC_WARPS = 4;
-
-struct WarpScratch {
-  double raw[2 * M3D_MAXC];  // raw pixels of the current point, per camera
-  Gram gc[M3D_MAXC];         // per-camera Gram contribution of the current point
-};
-
-template <bool FULL, bool PO>
-__global__ void __launch_bounds__(RANSAC_WARPS * 32)
-k_ransac(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t N,
-         int undistort, int min_cams, double thr, double init_best, double* __restrict__ p3d,
-         uint8_t* __restrict__ picked, double* __restrict__ xy_picked, double* __restrict__ err_out,
-         int32_t* __restrict__ subset_out, int32_t* __restrict__ neval_out) {
-  __shared__ WarpScratch scratch[RANSAC_WARPS];
-  const unsigned FULLM = 0xffffffffu;
-  const int C = rig.n_cams;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpScratch& ws = scratch[warp];
-  const int64_t tile0 = ((int64_t)blockIdx.x * RANSAC_WARPS + warp) * 32;
-  if (tile0 >= N) return;
-  const int64_t n = tile0 + lane;
-  const bool inb = n < N;
-  // first subset whose error is below T1 wins (see DESIGN.md "subset search")
-  const double T1 = thr < init_best ? thr : init_best;
-
-  // ---- phase A: lane = point; evaluate s = 0 (all valid cameras) -------------------------
-  uint32_t vmask = 0, umask = 0;
-  double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
-  int32_t best_s = -1, neval = 0;
-  uint32_t best_mask = 0;
-  bool done = !inb;
-  if (inb) {
-    Gram G;
-    gram_zero(G);
-#pragma unroll 1
-    for (int c = 0; c < C; ++c) {
-      const double2 p = ld_xy(xy, (int64_t)c * N + n);
-      if (p.x == p.x) {  // validity on the RAW x (cameras.py:658-659)
-        vmask |= 1u << c;
-        double x = p.x, y = p.y;
-        if (undistort) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
-        if (x == x) {  // survives inside triangulate (cameras.py:630)
-          umask |= 1u << c;
-          gram_add_camera(G, rig.cam[c], x, y);
-        }
-      }
-    }
-    const int k = __popc(vmask);
-    neval = 1;  // the full set is always tried (cameras.py:691)
-    if (__popc(umask) >= 2) {
-      double X, Y, Z;
-      dlt_solve(G, X, Y, Z);
-      double sum = 0.0;
-      int m = 0;
-      for (uint32_t rest = vmask; rest; rest &= rest - 1) {
-        const int c = __ffs(rest) - 1;
-        const double2 p = ld_xy(xy, (int64_t)c * N + n);
-        double u, v;
-        project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
-        const double e = residual_norm(p.x - u, p.y - v);
-        if (e == e) {
-          sum += e;
-          ++m;
-        }
-      }
-      const double e0 = (m >= 2) ? sum / (double)m : qnan();
-      if (e0 < best_err) {
-        best_err = e0;
-        best_s = 0;
-        best_mask = vmask;
-        bx = X;
-        by = Y;
-        bz = Z;
-        if (e0 < thr) done = true;
-      }
-    }
-    // every smaller subset is skipped when k <= min_cams (or k < 2: nothing to drop)
-    if (k < 2 || k <= min_cams) done = true;
-  }
-
-  // ---- phase B: one warp per unfinished point, one subset per lane ------------------------
-  uint32_t todo = __ballot_sync(FULLM, !done);
-  while (todo) {
-    const int p = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int64_t np = tile0 + p;
-    const uint32_t vm = __shfl_sync(FULLM, vmask, p);
-    const uint32_t um = __shfl_sync(FULLM, umask, p);
-    const int k = __popc(vm);
-    const uint32_t n_sub = 1u << k;
-    __syncwarp();
-    if (lane < C) {
-      const double2 q = ld_xy(xy, (int64_t)lane * N + np);
-      ws.raw[2 * lane] = q.x;
-      ws.raw[2 * lane + 1] = q.y;
-      Gram g;
-      gram_zero(g);
-      if ((um >> lane) & 1u) {
-        double x = q.x, y = q.y;
-        if (undistort) undistort_point<FULL, PO>(rig.cam[lane], q.x, q.y, x, y);
-        gram_add_camera(g, rig.cam[lane], x, y);
-      }
-      ws.gc[lane] = g;
-    }
-    __syncwarp();
-
-    // pass 1: first admissible s >= 1 with err < T1
-    bool found = false;
-    int32_t ne = 0;
-    for (uint32_t base = 0; base < n_sub; base += 32) {
-      const uint32_t s = base + lane;
-      uint32_t cm = 0;
-      bool adm = false;
-      if (s >= 1 && s < n_sub) {
-        cm = subset_mask(vm, k, s);
-        const int cnt = __popc(cm);
-        adm = (cnt >= min_cams) || (cnt == k);
-      }
-      double X = qnan(), Y = qnan(), Z = qnan(), e = pos_inf();
-      if (adm) e = eval_subset<FULL, PO>(rig, ws.raw, ws.gc, cm, um, T1, X, Y, Z);
-      const uint32_t hit = __ballot_sync(FULLM, adm && (e < T1));
-      const uint32_t admb = __ballot_sync(FULLM, adm);
-      if (hit) {
-        const int wl = __ffs(hit) - 1;
-        ne += __popc(admb & (0xffffffffu >> (31 - wl)));
-        const double we = __shfl_sync(FULLM, e, wl);
-        const double wx = __shfl_sync(FULLM, X, wl);
-        const double wy = __shfl_sync(FULLM, Y, wl);
-        const double wz = __shfl_sync(FULLM, Z, wl);
-        const uint32_t wm = __shfl_sync(FULLM, cm, wl);
-        if (lane == p) {
-          best_err = we;
-          best_s = (int32_t)(base + wl);
-          best_mask = wm;
-          bx = wx;
-          by = wy;
-          bz = wz;
-        }
-        found = true;
-        break;
-      }
-      ne += __popc(admb);
-    }
-    if (lane == p) neval += ne;
-    if (found) continue;
-
-    // pass 2 (no subset under T1): strict arg-min over all admissible subsets, first wins
-    // on ties; pruning against the running best keeps it exact.
-    double rb = __shfl_sync(FULLM, best_err, p);
-    for (uint32_t base = 0; base < n_sub; base += 32) {
-      const uint32_t s = base + lane;
-      uint32_t cm = 0;
-      bool adm = false;
-      if (s >= 1 && s < n_sub) {
-        cm = subset_mask(vm, k, s);
-        const int cnt = __popc(cm);
-        adm = (cnt >= min_cams) || (cnt == k);
-      }
-      double X = qnan(), Y = qnan(), Z = qnan(), e = pos_inf();
-      if (adm) e = eval_subset<FULL, PO>(rig, ws.raw, ws.gc, cm, um, rb, X, Y, Z);
-      if (!(e < rb)) e = pos_inf();  // NaN / pruned / not better
-      // warp arg-min on (e, lane): lowest lane wins ties
-      double me = e;
-      int ml = lane;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double oe = __shfl_xor_sync(FULLM, me, off);
-        const int ol = __shfl_xor_sync(FULLM, ml, off);
-        if (oe < me || (oe == me && ol < ml)) {
-          me = oe;
-          ml = ol;
-        }
-      }
-      if (me < rb) {
-        rb = me;
-        const double wx = __shfl_sync(FULLM, X, ml);
-        const double wy = __shfl_sync(FULLM, Y, ml);
-        const double wz = __shfl_sync(FULLM, Z, ml);
-        const uint32_t wm = __shfl_sync(FULLM, cm, ml);
-        if (lane == p) {
-          best_err = me;
-          best_s = (int32_t)(base + ml);
-          best_mask = wm;
-          bx = wx;
-          by = wy;
-          bz = wz;
-        }
-      }
-    }
-  }
-
-  // ---- outputs: lane = point again, coalesced per plane -------------------------------------
-  if (inb) {
-    p3d[3 * n] = bx;
-    p3d[3 * n + 1] = by;
-    p3d[3 * n + 2] = bz;
-    err_out[n] = (best_s >= 0) ? best_err : 0.0;  // errors default to 0.0 (cameras.py:675)
-    if (subset_out) subset_out[n] = best_s;
-    if (neval_out) neval_out[n] = neval;
-    if (picked || xy_picked) {
-#pragma unroll 1
-      for (int c = 0; c < C; ++c) {
-        const bool in = (best_mask >> c) & 1u;
-        if (picked) picked[(int64_t)c * N + n] = in ? 1 : 0;
-        if (xy_picked) {
-          double2 q = make_double2(qnan(), qnan());
-          if (in) q = ld_xy(xy, (int64_t)c * N + n);
-          st_xy(xy_picked, (int64_t)c * N + n, q.x, q.y);
-        }
-      }
-    }
-  }
-}
+#include "m3d_ransac.cuh"
 
 // ---------------------------------------------------------------------------------------
 // fp64 FMA peak probe (the second roofline of this path)
@@ -550,6 +375,16 @@ int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig*
     return fail(M3D_ERR_INVALID, "m3d_rig_create: " + why);
   }
   rig->device = device;
+  {
+    DeviceGuard g(device);
+    cudaError_t e = cudaMalloc(&rig->dev_g, sizeof(RigDev));
+    if (e == cudaSuccess) e = cudaMemcpy(rig->dev_g, &rig->dev, sizeof(RigDev), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(rig->dev_g);
+      delete rig;
+      return fail(M3D_ERR_CUDA, std::string("m3d_rig_create: ") + cudaGetErrorString(e));
+    }
+  }
   *out = rig;
   return M3D_OK;
 }
@@ -577,6 +412,7 @@ void m3d_rig_destroy(m3d_rig* rig) {
   {
     DeviceGuard g(rig->device);
     free_workspace(rig);
+    cudaFree(rig->dev_g);
   }
   delete rig;
 }
@@ -674,18 +510,28 @@ int m3d_project(const m3d_rig* rig, const double* p3d, int64_t N, double* out, v
 static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, int undistort,
                               double* p3d, double* err, cudaStream_t st, int sms) {
   const int grid = grid_for(N, 256, sms);
-#define CALL(F, P)                                                                          \
-  do {                                                                                      \
-    if (undistort) {                                                                        \
-      if (err) k_triangulate<F, P, true, true><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
-      else k_triangulate<F, P, true, false><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);    \
-    } else {                                                                                \
-      if (err) k_triangulate<F, P, false, true><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
-      else k_triangulate<F, P, false, false><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);   \
-    }                                                                                       \
+  static const int variant = getenv("M3D_TRI_VARIANT") ? atoi(getenv("M3D_TRI_VARIANT")) : 0;
+  const int C = rig->dev.n_cams;
+#define CALLV(F, P, NC, MB)                                                                         \
+  do {                                                                                              \
+    if (undistort) {                                                                                \
+      if (err) k_triangulate<F, P, true, true, NC, MB><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
+      else k_triangulate<F, P, true, false, NC, MB><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);    \
+    } else {                                                                                        \
+      if (err) k_triangulate<F, P, false, true, NC, MB><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err); \
+      else k_triangulate<F, P, false, false, NC, MB><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);   \
+    }                                                                                               \
+  } while (0)
+#define CALL(F, P)                                          \
+  do {                                                      \
+    if (C == 8 && variant == 0) CALLV(F, P, 8, 2);          \
+    else if (C == 8 && variant == 1) CALLV(F, P, 8, 3);     \
+    else if (C == 8 && variant == 2) CALLV(F, P, 8, 4);     \
+    else CALLV(F, P, 0, 3);                                 \
   } while (0)
   M3D_DISPATCH_MODEL(rig, CALL);
 #undef CALL
+#undef CALLV
   return check_launch("k_triangulate");
 }
 
@@ -728,15 +574,31 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
                          double threshold, double init_best, double* p3d, uint8_t* picked,
                          double* xy_picked, double* err, int32_t* subset, int32_t* neval,
                          cudaStream_t st) {
-  const int64_t per_block = RANSAC_WARPS * 32;
+  const int64_t per_block = RANSAC_THREADS;
   const int64_t blocks = (N + per_block - 1) / per_block;
   if (blocks > 0x7fffffffLL) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: N too large for one launch");
-#define CALL(F, P)                                                                              \
-  k_ransac<F, P><<<(unsigned)blocks, RANSAC_WARPS * 32, 0, st>>>(rig->dev, xy, N, undistort, min_cams, \
-                                                                 threshold, init_best, p3d, picked,    \
-                                                                 xy_picked, err, subset, neval)
+  static const int variant = getenv("M3D_RANSAC_VARIANT") ? atoi(getenv("M3D_RANSAC_VARIANT")) : 0;
+  const int C = rig->dev.n_cams;
+  const size_t smem = ransac_smem_bytes(C > 0 ? C : 1);
+#define CALLV(F, P, NC, MB)                                                                        \
+  do {                                                                                             \
+    auto kfn = k_ransac<F, P, NC, MB>;                                                             \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem, st>>>(rig->dev, rig->dev_g, xy, N, undistort, min_cams, \
+                                                        threshold, init_best, p3d, picked, xy_picked, err, \
+                                                        subset, neval);                                    \
+  } while (0)
+#define CALL(F, P)                                          \
+  do {                                                      \
+    if (C == 8 && variant == 0) CALLV(F, P, 8, 3);          \
+    else if (C == 8 && variant == 1) CALLV(F, P, 8, 4);     \
+    else if (C == 8 && variant == 2) CALLV(F, P, 8, 5);     \
+    else if (C == 8 && variant == 3) CALLV(F, P, 8, 6);     \
+    else CALLV(F, P, 0, 4);                                 \
+  } while (0)
   M3D_DISPATCH_MODEL(rig, CALL);
 #undef CALL
+#undef CALLV
   return check_launch("k_ransac");
 }
 

@@ -55,6 +55,49 @@ M3D_HD double qnan() {
 #endif
 }
 
+// Reciprocal / square root.  CUDA's IEEE-rounded double division and sqrt expand to a
+// MUFU seed, Newton steps and a subroutine CALL on every use (measured: 46 CALLs per
+// joint-instance in the DLT kernel).  On the device we take the hardware seed
+// (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20) and two Newton steps (2^-40, 2^-80), branch-free:
+// the result is within 1 ulp of the IEEE value, far inside the parity budget of the path
+// (the reference's own LAPACK solve carries ~1e-10 px).  Special operands: NaN -> NaN as
+// in IEEE; 0, inf and denormal operands give NaN instead of inf / 0 — every call site
+// either guards them (z == 0 in projectPoints, zero residual) or is already in
+// garbage-in territory where the reference's own result is inf/NaN noise.
+M3D_HD double rcp(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+#else
+  return 1.0 / a;
+#endif
+}
+
+M3D_HD double sqrt_fast(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y;        // ~ sqrt(a)
+  double h = 0.5 * y;      // ~ 1 / (2 sqrt(a))
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, a);
+  g = fma(d, h, g);
+  return (a == 0.0) ? 0.0 : g;   // exact zero residual stays zero
+#else
+  return sqrt(a);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // undistortion: pixel -> normalised coordinates
 // ---------------------------------------------------------------------------------------
@@ -64,11 +107,11 @@ M3D_HD double qnan() {
 // cvUndistortPointsInternal, TermCriteria(MAX_ITER, 5)).  FULL = rational (k4..k6) and
 // thin-prism (s1..s4) terms present.
 template <bool FULL>
-M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+M3D_HD void undistort_pinhole_exact(const CamDev& c, double u, double v, double& xo, double& yo) {
+  // literal transcription, taken only when the icdist < 0 bail-out fires
   const double x0 = (u - c.cx) * c.ifx;
   const double y0 = (v - c.cy) * c.ify;
   double x = x0, y = y0;
-#pragma unroll
   for (int j = 0; j < 5; ++j) {
     const double r2 = x * x + y * y;
     double icdist;
@@ -92,6 +135,34 @@ M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, d
     x = (x0 - dx) * icdist;
     y = (y0 - dy) * icdist;
   }
+  xo = x;
+  yo = y;
+}
+
+template <bool FULL>
+M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double x0 = (u - c.cx) * c.ifx;
+  const double y0 = (v - c.cy) * c.ify;
+  double x = x0, y = y0;
+  bool bail = false;  // OpenCV: "if (icdist < 0) { x = x0; y = y0; break; }"
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    double icdist = rcp(1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
+    if (FULL) icdist *= 1.0 + ((c.k[7] * r2 + c.k[6]) * r2 + c.k[5]) * r2;
+    bail = bail || (icdist < 0.0);
+    const double x2 = x + x, y2 = y + y;
+    const double xy2 = x2 * y;
+    double dx = c.k[2] * xy2 + c.k[3] * (x2 * x + r2);
+    double dy = c.k[3] * xy2 + c.k[2] * (y2 * y + r2);
+    if (FULL) {
+      dx += c.k[8] * r2 + c.k[9] * r2 * r2;
+      dy += c.k[10] * r2 + c.k[11] * r2 * r2;
+    }
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  if (bail) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
   xo = x;
   yo = y;
 }
@@ -197,7 +268,7 @@ M3D_HD void distort_pinhole(const CamDev& c, double x, double y, double& u, doub
   double cdist = 1.0 + c.k[0] * r2 + c.k[1] * r4 + c.k[4] * r6;
   double xd, yd;
   if (FULL) {
-    const double icdist2 = 1.0 / (1.0 + c.k[5] * r2 + c.k[6] * r4 + c.k[7] * r6);
+    const double icdist2 = rcp(1.0 + c.k[5] * r2 + c.k[6] * r4 + c.k[7] * r6);
     xd = x * cdist * icdist2 + c.k[2] * a1 + c.k[3] * a2 + c.k[8] * r2 + c.k[9] * r4;
     yd = y * cdist * icdist2 + c.k[2] * a3 + c.k[3] * a1 + c.k[10] * r2 + c.k[11] * r4;
   } else {
@@ -213,7 +284,7 @@ template <bool FULL>
 M3D_HD void project_pinhole(const CamDev& c, double X, double Y, double Z, double& u, double& v) {
   double xc, yc, zc;
   to_camera(c, X, Y, Z, xc, yc, zc);
-  const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
+  const double iz = (zc != 0.0) ? rcp(zc) : 1.0;
   distort_pinhole<FULL>(c, xc * iz, yc * iz, u, v);
 }
 
@@ -276,7 +347,7 @@ M3D_HD void distort_point(const CamDev& c, double x, double y, double& u, double
 }
 
 // residual norm exactly as np.linalg.norm(axis=2): sqrt(ex*ex + ey*ey)
-M3D_HD double residual_norm(double ex, double ey) { return sqrt(ex * ex + ey * ey); }
+M3D_HD double residual_norm(double ex, double ey) { return sqrt_fast(ex * ex + ey * ey); }
 
 // ---------------------------------------------------------------------------------------
 // DLT normal equations.  For camera rows a1 = x*M[2]-M[0], a2 = y*M[2]-M[1] (M = [R|t])
@@ -391,6 +462,7 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
   double x0 = 0.0, x1 = 0.0, x2 = 0.0;
   bool ok = false;
   const double tr = G.h[0] + G.h[3] + G.h[5];
+  const double itr2 = rcp(tr * tr);
 #pragma unroll 1
   for (int it = 0; it < 12; ++it) {
     const double a = G.h[0] - lam, b = G.h[1], c = G.h[2], d = G.h[3] - lam, e = G.h[4],
@@ -400,16 +472,16 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
     const double det = a * c00 + b * c01 + c * c02;
     // positive definite (Sylvester) <=> lam < lam_min(H): we are on the right branch
     if (!(a > 0.0 && c22 > 0.0 && det > 0.0)) break;
-    const double idet = 1.0 / det;
+    const double idet = rcp(det);
     x0 = -(c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2]) * idet;
     x1 = -(c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2]) * idet;
     x2 = -(c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2]) * idet;
     const double fl = G.w - lam + (G.g[0] * x0 + G.g[1] * x1 + G.g[2] * x2);
     const double n2 = 1.0 + x0 * x0 + x1 * x1 + x2 * x2;
-    const double dl = fl / n2;
+    const double dl = fl * rcp(n2);
     // lam_min(H - lam I) >= det / tr^2 ; a step below 1e-7 of that changes X by < 1e-14 |X|
     // beyond the first-order correction applied here.
-    const double mu_lb = det / (tr * tr);
+    const double mu_lb = det * itr2;
     if (fabs(dl) <= 1e-7 * mu_lb) {
       // first-order update X(lam + dl) = X + dl (H - lam I)^-1 X
       const double y0 = (c00 * x0 + c01 * x1 + c02 * x2) * idet;
@@ -429,7 +501,8 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
     Y = x1;
     Z = x2;
   } else {
-    dlt_solve_jacobi(G, X, Y, Z);
+    const Gram tmp = G;  // the copy (not G) is what lives in local memory for the call
+    dlt_solve_jacobi(tmp, X, Y, Z);
   }
 }
 
