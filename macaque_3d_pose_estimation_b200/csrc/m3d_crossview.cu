@@ -3,9 +3,7 @@
 //                    deproject (:327-355) and calc_dist_btw_lines (:359-369) fused, one CTA
 //                    per frame, rays staged in shared memory;
 //   k_match_svt    : matchSVT (step2_crossviewmatching.py:130-216), one CTA per frame, the
-//                    ADMM iterate and a cyclic-Jacobi symmetric eigensolver held in shared
-//                    memory (the iterate Y/mu + X stays symmetric, so the reference's SVD
-//                    shrinkage U max(s - lambda/mu, 0) V^T equals V sign(L) max(|L| - lambda/mu, 0) V^T).
+//                    ADMM iterate and a one-sided Jacobi SVD of it held in shared memory.
 #include <cuda_runtime.h>
 
 #include <string>
@@ -107,7 +105,9 @@ k_ray_affinity(const __grid_constant__ RigDev rig, const double* __restrict__ kp
     const int i = e / M, j = e % M;
     if (i > j) continue;
     double d = 300.0;  // Dth2 * 2
-    if (i == j) {
+    if (camof[i] < 0 || camof[j] < 0) {
+      d = 300.0;  // padding rows / columns: outside the frame's (n x n) matrix
+    } else if (i == j) {
       d = 0.0;
     } else {
       const int ci = camof[i], cj = camof[j];
@@ -138,7 +138,7 @@ k_ray_affinity(const __grid_constant__ RigDev rig, const double* __restrict__ kp
   double s = 0.0, cntv = 0.0;
   for (int e = tid; e < M * M; e += AFF_THREADS) {
     const double d = D[e];
-    if (d < 300.0) {
+    if (d < 300.0) {  // padding entries are 300 and never counted
       s += d;
       cntv += 1.0;
     }
@@ -158,6 +158,192 @@ k_ray_affinity(const __grid_constant__ RigDev rig, const double* __restrict__ kp
     double a = 1.0 / (1.0 + exp(-5.0 * z));
     if (d > 150.0) a = 0.0;
     A[e] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: matchSVT — ADMM with singular-value thresholding, one CTA per frame (persistent CTAs
+// loop over frames).  The SVD of the M x M iterate is a one-sided (Hestenes) Jacobi on its
+// columns, held in shared memory: A V = U S with orthogonal columns, so the reference's
+// Q = U max(S - lambda/mu, 0) V^T is sum_j max(s_j - tau, 0)/s_j * (A v_j) v_j^T.
+// ---------------------------------------------------------------------------------------
+constexpr int SVT_THREADS = 256;
+constexpr int SVT_MAX_M = 112;
+
+__global__ void __launch_bounds__(SVT_THREADS)
+k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, int F, int M, int C,
+            double alpha, double lambda, double mu0, double tol, int max_iter,
+            uint8_t* __restrict__ match, int32_t* __restrict__ iters, double* __restrict__ wsall, int ld) {
+  extern __shared__ double sm[];
+  double* B = sm;                          // [Me][ld] columns of the iterate (col-major)
+  double* V = B + (size_t)ld * (M + 1);    // [Me][ld] accumulated rotations
+  double* sig = V + (size_t)ld * (M + 1);  // [Me] singular values -> shrink weights
+  double* red = sig + (M + 1);             // [>=32] reduction scratch
+  int* flag = reinterpret_cast<int*>(red + 40);
+  const int tid = threadIdx.x;
+  double* X = wsall + (size_t)blockIdx.x * 5 * M * M;
+  double* X0 = X + (size_t)M * M;
+  double* Y = X0 + (size_t)M * M;
+  double* Wm = Y + (size_t)M * M;
+  double* Q = Wm + (size_t)M * M;
+
+  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+    const int32_t* dg = dim + (size_t)f * (C + 1);
+    const int n = dg[C] < M ? dg[C] : M;  // real detections of this frame
+    const double* Wf = Wall + (size_t)f * M * M;
+    uint8_t* out = match + (size_t)f * M * M;
+    for (int e = tid; e < M * M; e += SVT_THREADS) out[e] = 0;
+    if (n <= 0) {
+      if (iters && tid == 0) iters[f] = 0;
+      continue;
+    }
+    const int ne = n + (n & 1);  // even size for the tournament schedule (dummy column = n)
+    const int npairs = ne / 2;
+    int g = 32;
+    while (g > 1 && g * npairs > SVT_THREADS) g >>= 1;
+    const int pair_of = tid / g, sub = tid % g;
+    const bool jactive = pair_of < npairs;
+    // S = W with zero diagonal, symmetrised; X = S; Y = 0; Wm = alpha - S   (step2:150-157)
+    for (int e = tid; e < n * n; e += SVT_THREADS) {
+      const int i = e / n, j = e % n;
+      const double a = (i == j) ? 0.0 : Wf[i * M + j];
+      const double b = (i == j) ? 0.0 : Wf[j * M + i];
+      const double sv = (a + b) / 2.0;
+      X[e] = sv;
+      Y[e] = 0.0;
+      Wm[e] = alpha - sv;
+    }
+    __syncthreads();
+    double mu = mu0;
+    int it = 0;
+    for (it = 0; it < max_iter; ++it) {
+      // B = Y/mu + X (column j of the iterate in B[j]), V = I
+      for (int e = tid; e < ne * ne; e += SVT_THREADS) {
+        const int j = e / ne, i = e % ne;
+        double a = 0.0;
+        if (i < n && j < n) a = Y[i * n + j] / mu + X[i * n + j];
+        B[j * ld + i] = a;
+        V[j * ld + i] = (i == j) ? 1.0 : 0.0;
+      }
+      for (int e = tid; e < n * n; e += SVT_THREADS) X0[e] = X[e];
+      __syncthreads();
+      // one-sided Jacobi sweeps
+      for (int sweep = 0; sweep < 40; ++sweep) {
+        if (tid == 0) *flag = 0;
+        __syncthreads();
+        for (int r = 0; r < ne - 1; ++r) {
+          const unsigned gmask = __ballot_sync(0xffffffffu, jactive);  // lanes that own a column pair
+          if (jactive) {
+            int p, q;
+            if (pair_of == 0) {
+              p = ne - 1;
+              q = r;
+            } else {
+              p = (r + pair_of) % (ne - 1);
+              q = (r - pair_of + (ne - 1)) % (ne - 1);
+            }
+            double* bp = B + (size_t)p * ld;
+            double* bq = B + (size_t)q * ld;
+            double aa = 0.0, bb = 0.0, ab = 0.0;
+            for (int i = sub; i < ne; i += g) {
+              const double x = bp[i], y = bq[i];
+              aa += x * x;
+              bb += y * y;
+              ab += x * y;
+            }
+            for (int off = g >> 1; off > 0; off >>= 1) {
+              aa += __shfl_xor_sync(gmask, aa, off, 32);
+              bb += __shfl_xor_sync(gmask, bb, off, 32);
+              ab += __shfl_xor_sync(gmask, ab, off, 32);
+            }
+            if (fabs(ab) > 1e-15 * sqrt(aa * bb) && ab != 0.0) {
+              const double zeta = (bb - aa) / (2.0 * ab);
+              const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+              const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+              double* vp = V + (size_t)p * ld;
+              double* vq = V + (size_t)q * ld;
+              for (int i = sub; i < ne; i += g) {
+                const double x = bp[i], y = bq[i];
+                bp[i] = cs * x - sn * y;
+                bq[i] = sn * x + cs * y;
+                const double vx = vp[i], vy = vq[i];
+                vp[i] = cs * vx - sn * vy;
+                vq[i] = sn * vx + cs * vy;
+              }
+              if (sub == 0) *flag = 1;
+            }
+          }
+          __syncthreads();
+        }
+        const int rotated = *flag;
+        __syncthreads();
+        if (!rotated) break;
+      }
+      // shrink weights  max(s_j - lambda/mu, 0) / s_j
+      const double tau = lambda / mu;
+      for (int j = tid; j < ne; j += SVT_THREADS) {
+        double ss = 0.0;
+        for (int i = 0; i < ne; ++i) ss += B[j * ld + i] * B[j * ld + i];
+        const double sv = sqrt(ss);
+        sig[j] = (sv > tau) ? (sv - tau) / sv : 0.0;
+      }
+      __syncthreads();
+      // Q = sum_j w_j b_j v_j^T ; X = Q - (Wm + Y)/mu, zero same-camera blocks, diag = 1, clip
+      for (int e = tid; e < n * n; e += SVT_THREADS) {
+        const int i = e / n, j = e % n;
+        double q = 0.0;
+        for (int c = 0; c < ne; ++c) {
+          const double w = sig[c];
+          if (w != 0.0) q += w * B[c * ld + i] * V[c * ld + j];
+        }
+        Q[e] = q;
+        double x = q - (Wm[e] + Y[e]) / mu;
+        int ci = -1, cj = -1;
+        for (int c = 0; c <= C; ++c) {
+          if (dg[c] <= i) ci = c;
+          if (dg[c] <= j) cj = c;
+        }
+        if (ci == cj) x = 0.0;             // X[i0:i1, i0:i1] = 0  (step2:170-172)
+        if (i == j) x = 1.0;               // pselect == 1
+        x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
+        X[e] = x;
+      }
+      __syncthreads();
+      // X = (X + X^T)/2 ; Y += mu (X - Q) ; residuals
+      double pr = 0.0, dr = 0.0;
+      for (int e = tid; e < n * n; e += SVT_THREADS) {
+        const int i = e / n, j = e % n;
+        if (i <= j) {
+          const double xs = (X[i * n + j] + X[j * n + i]) / 2.0;
+          // stage the symmetric value in the unused half of B (shared) to avoid a race
+          B[(size_t)i * ld + j] = xs;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < n * n; e += SVT_THREADS) {
+        const int i = e / n, j = e % n;
+        const double xs = (i <= j) ? B[(size_t)i * ld + j] : B[(size_t)j * ld + i];
+        const double q = Q[e];
+        X[e] = xs;
+        Y[e] += mu * (xs - q);
+        pr += (xs - q) * (xs - q);
+        const double d = xs - X0[e];
+        dr += d * d;
+      }
+      const double pRes = sqrt(block_sum<SVT_THREADS>(pr, red)) / (double)n;
+      const double dRes = mu * sqrt(block_sum<SVT_THREADS>(dr, red)) / (double)n;
+      if (pRes < tol && dRes < tol) break;
+      if (pRes > 10.0 * dRes) mu *= 2.0;
+      else if (dRes > 10.0 * pRes) mu /= 2.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += SVT_THREADS) {
+      const int i = e / n, j = e % n;
+      const double xs = (X[i * n + j] + X[j * n + i]) / 2.0;
+      out[i * M + j] = xs > 0.5 ? 1 : 0;
+    }
+    if (iters && tid == 0) iters[f] = it < max_iter ? it : max_iter - 1;
+    __syncthreads();
   }
 }
 
@@ -183,9 +369,36 @@ int m3d_ray_affinity(const m3d_rig* rig, const double* kp, const int32_t* dim, i
 int m3d_match_svt(const double* W, const int32_t* dim, int32_t F, int32_t M, int32_t C, double alpha,
                   double lambda, double mu, double tol, int32_t max_iter, uint8_t* match,
                   int32_t* iters, int32_t device, void* stream) {
-  (void)W; (void)dim; (void)F; (void)M; (void)C; (void)alpha; (void)lambda; (void)mu; (void)tol;
-  (void)max_iter; (void)match; (void)iters; (void)device; (void)stream;
-  return m3d_fail(M3D_ERR_INVALID, "m3d_match_svt: not implemented yet");
+  if (F < 0 || M < 0 || C < 0) return m3d_fail(M3D_ERR_INVALID, "m3d_match_svt: negative size");
+  if (M > SVT_MAX_M)
+    return m3d_fail(M3D_ERR_INVALID, "m3d_match_svt: more than " + std::to_string(SVT_MAX_M) +
+                                         " detections per frame are not supported");
+  if (C > M3D_MAX_CAMS) return m3d_fail(M3D_ERR_INVALID, "m3d_match_svt: too many cameras");
+  if (F == 0 || M == 0) return M3D_OK;
+  if (!W || !dim || !match) return m3d_fail(M3D_ERR_INVALID, "m3d_match_svt: NULL buffer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return m3d_fail(M3D_ERR_NO_GPU, "m3d_match_svt: no CUDA device visible; libm3d has no CPU fallback");
+  M3dDeviceGuard guard(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int ld = (M + 1) | 1;  // odd column stride: conflict-free column access
+  const size_t smem = sizeof(double) * (2 * (size_t)ld * (M + 1) + 3 * (size_t)(M + 1) + 64);
+  cudaError_t e = cudaFuncSetAttribute(k_match_svt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("k_match_svt smem: ") + cudaGetErrorString(e));
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = sms * per_sm;
+  if (grid > F) grid = F;
+  double* ws = nullptr;  // per-CTA global scratch: X, X0, Y, Wm, Q
+  e = cudaMallocAsync(&ws, sizeof(double) * 5 * (size_t)M * M * grid, st);
+  if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("m3d_match_svt workspace: ") + cudaGetErrorString(e));
+  k_match_svt<<<grid, SVT_THREADS, smem, st>>>(W, dim, F, M, C, alpha, lambda, mu, tol, max_iter, match, iters, ws, ld);
+  int rc = m3d_check_launch("k_match_svt");
+  cudaFreeAsync(ws, st);
+  return rc;
 }
 
 }  // extern "C"

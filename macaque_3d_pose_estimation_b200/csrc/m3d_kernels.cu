@@ -510,7 +510,6 @@ int m3d_project(const m3d_rig* rig, const double* p3d, int64_t N, double* out, v
 static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, int undistort,
                               double* p3d, double* err, cudaStream_t st, int sms) {
   const int grid = grid_for(N, 256, sms);
-  static const int variant = getenv("M3D_TRI_VARIANT") ? atoi(getenv("M3D_TRI_VARIANT")) : 0;
   const int C = rig->dev.n_cams;
 #define CALLV(F, P, NC, MB)                                                                         \
   do {                                                                                              \
@@ -522,11 +521,11 @@ static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, i
       else k_triangulate<F, P, false, false, NC, MB><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);   \
     }                                                                                               \
   } while (0)
+  // measured on B200 (profiles/): the 8-camera unrolled kernel is fastest at 128 registers
+  // (2 CTAs/SM, no spills); the run-time-C kernel at 80 registers (3 CTAs/SM)
 #define CALL(F, P)                                          \
   do {                                                      \
-    if (C == 8 && variant == 0) CALLV(F, P, 8, 2);          \
-    else if (C == 8 && variant == 1) CALLV(F, P, 8, 3);     \
-    else if (C == 8 && variant == 2) CALLV(F, P, 8, 4);     \
+    if (C == 8) CALLV(F, P, 8, 2);                          \
     else CALLV(F, P, 0, 3);                                 \
   } while (0)
   M3D_DISPATCH_MODEL(rig, CALL);
@@ -577,7 +576,6 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
   const int64_t per_block = RANSAC_THREADS;
   const int64_t blocks = (N + per_block - 1) / per_block;
   if (blocks > 0x7fffffffLL) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: N too large for one launch");
-  static const int variant = getenv("M3D_RANSAC_VARIANT") ? atoi(getenv("M3D_RANSAC_VARIANT")) : 0;
   const int C = rig->dev.n_cams;
   const size_t smem = ransac_smem_bytes(C > 0 ? C : 1);
 #define CALLV(F, P, NC, MB)                                                                        \
@@ -590,10 +588,7 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
   } while (0)
 #define CALL(F, P)                                          \
   do {                                                      \
-    if (C == 8 && variant == 0) CALLV(F, P, 8, 3);          \
-    else if (C == 8 && variant == 1) CALLV(F, P, 8, 4);     \
-    else if (C == 8 && variant == 2) CALLV(F, P, 8, 5);     \
-    else if (C == 8 && variant == 3) CALLV(F, P, 8, 6);     \
+    if (C == 8) CALLV(F, P, 8, 4);                          \
     else CALLV(F, P, 0, 4);                                 \
   } while (0)
   M3D_DISPATCH_MODEL(rig, CALL);

@@ -32,8 +32,9 @@ constexpr int RANSAC_WARPS = 4;
 constexpr int RANSAC_THREADS = RANSAC_WARPS * 32;
 
 __host__ __device__ inline size_t ransac_rig_bytes() { return (sizeof(RigDev) + 15) & ~size_t(15); }
+// per warp: U[C][32] double2 | raw[C][2] | gc[C] Gram | glow[10][32] doubles
 __host__ __device__ inline size_t ransac_warp_bytes(int C) {
-  return (size_t)C * 32 * 16 + (size_t)C * 16 + (size_t)C * sizeof(Gram);
+  return (size_t)C * 32 * 16 + (size_t)C * 16 + (size_t)C * sizeof(Gram) + 10 * 32 * 8;
 }
 inline size_t ransac_smem_bytes(int C) { return ransac_rig_bytes() + RANSAC_WARPS * ransac_warp_bytes(C); }
 
@@ -64,6 +65,7 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
   double2* Us = reinterpret_cast<double2*>(wbase);                    // [C][32] undistorted
   double* raws = reinterpret_cast<double*>(wbase + (size_t)C * 512);  // [C][2] raw, current point
   Gram* gcs = reinterpret_cast<Gram*>(wbase + (size_t)C * 512 + (size_t)C * 16);  // [C]
+  double* glow = reinterpret_cast<double*>(wbase + (size_t)C * 512 + (size_t)C * 16 + (size_t)C * sizeof(Gram));
 
   // rig copy for per-lane camera indexing (constant-bank reads with lane-varying addresses
   // would serialise)
@@ -245,6 +247,33 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
     }
     __syncwarp();
 
+    // Two-level subset structure of one 32-subset step: the low min(k,5) bits of s (the
+    // LAST valid cameras) vary across lanes, the high bits (the first valid cameras) are
+    // shared by the whole step.  Per lane, once per point: camera mask and Gram block of
+    // the low part.
+    const int klow = k < 5 ? k : 5;
+    uint32_t vlow = 0;  // the klow highest-index valid cameras
+    {
+      uint32_t rest = vm;
+      for (int j = 0; j < k - klow; ++j) rest &= rest - 1;
+      vlow = rest;
+    }
+    const uint32_t vhigh = vm & ~vlow;
+    const int khigh = k - klow;
+    const uint32_t cm_low = subset_mask(vlow, klow, (uint32_t)lane & ((1u << klow) - 1u));
+    {
+      Gram g;
+      gram_zero(g);
+      for (uint32_t rest = cm_low & um; rest; rest &= rest - 1) gram_add(g, gcs[__ffs(rest) - 1]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) glow[i * 32 + lane] = g.h[i];
+      glow[6 * 32 + lane] = g.g[0];
+      glow[7 * 32 + lane] = g.g[1];
+      glow[8 * 32 + lane] = g.g[2];
+      glow[9 * 32 + lane] = g.w;
+    }
+    __syncwarp();
+
     double rb = T1;  // pass 1: fixed threshold T1; pass 2: running best
     bool found = false;
     int32_t ne = 0;
@@ -254,10 +283,11 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
 #pragma unroll 1
       for (uint32_t base = 0; base < n_sub && !found; base += 32) {
         const uint32_t s = base + lane;
+        const uint32_t cm_high = subset_mask(vhigh, khigh, base >> 5);  // warp-uniform
         uint32_t cm = 0;
         bool adm = false;
         if (s >= 1 && s < n_sub) {
-          cm = subset_mask(vm, k, s);
+          cm = cm_high | cm_low;
           const int cnt = __popc(cm);
           adm = (cnt >= min_cams) || (cnt == k);
         }
@@ -267,8 +297,13 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
         bool alive = adm && (__popc(cm & um) >= 2);
         if (alive) {
           Gram G;
-          gram_zero(G);
-          for (uint32_t rest = cm & um; rest; rest &= rest - 1) gram_add(G, gcs[__ffs(rest) - 1]);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) G.h[i] = glow[i * 32 + lane];
+          G.g[0] = glow[6 * 32 + lane];
+          G.g[1] = glow[7 * 32 + lane];
+          G.g[2] = glow[8 * 32 + lane];
+          G.w = glow[9 * 32 + lane];
+          for (uint32_t rest = cm_high & um; rest; rest &= rest - 1) gram_add(G, gcs[__ffs(rest) - 1]);
           dlt_solve(G, X, Y, Z);
           alive = (X == X);
         }
@@ -296,15 +331,14 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
             project_point<FULL, PO>(srig.cam[lane], Xl, Yl, Zl, u, v);
             e = residual_norm(raws[2 * lane] - u, raws[2 * lane + 1] - v);
           }
-          double sum = 0.0;
-          int m = 0;
-          for (int c = 0; c < C; ++c) {  // ordered sum, ascending camera (cameras.py:775)
-            const double ec = __shfl_sync(FULLM, e, c);
-            if (ec == ec) {
-              sum += ec;
-              ++m;
-            }
-          }
+          // fixed-shape butterfly over the camera lanes: NaN residuals count as 0 and drop out
+          // of the denominator (cameras.py:771-775); for 8 cameras this is numpy's pairwise
+          // order ((e0+e1)+(e2+e3))+((e4+e5)+(e6+e7))
+          const int m = __popc(__ballot_sync(FULLM, e == e));
+          double sum = (e == e) ? e : 0.0;
+#pragma unroll
+          for (int off = 1; off < M3D_MAXC; off <<= 1) sum += __shfl_xor_sync(FULLM, sum, off);
+          sum = __shfl_sync(FULLM, sum, 0);
           const double el = (m >= 2) ? sum / (double)m : qnan();
           if (el < rb) {
             if (lane == p) {
