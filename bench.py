@@ -311,6 +311,10 @@ def run_gpu(args):
     gather_ms = None
     if world > 1:
         from macaque_3d_pose_estimation_b200 import sharding
+        small = torch.zeros((world * 8,), dtype=torch.float64, device=device)
+        dist.all_reduce(small)                                 # communicator set-up outside the timing
+        out = sharding.gather_results([p3d, err], F, dst=0)    # one untimed gather (NCCL warm-up)
+        del out
         torch.cuda.synchronize()
         dist.barrier()
         g0 = torch.cuda.Event(enable_timing=True)
@@ -324,12 +328,6 @@ def run_gpu(args):
         gather_ms = float(tg.item())
         del out
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
     peak, peak_kind = measured_peaks()
     bpi = BYTES_PER_INSTANCE[args.workload](C)
     achieved = bpi * N / (ms_per_step * 1e-3) / 1e9            # per-GPU kernel, GB/s
@@ -338,15 +336,22 @@ def run_gpu(args):
                 "kernel": "k_triangulate<undistort,err>" if args.workload == "dlt" else "k_ransac",
                 "algorithmic_bytes_per_instance": bpi,
                 "note": "path is fp64-ALU bound at reference precision (SURVEY 7); see fp64"}
+    try:   # DRAM traffic per launch from the committed ncu capture (profiles/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
+        roofline["traffic"] = tj["dram_bytes_per_instance"] * N
+        roofline["traffic_source"] = tj["source"]
+    except Exception:
+        pass
     tf = ctypes_double()
-    if lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
+    if rank == 0 and lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
         roofline["fp64_peak_tflops_measured"] = tf.value
     extra = {}
     if args.workload == "ransac":
         extra["mean_subsets_per_point"] = float(nev.double().mean().item())
         extra["selected_fraction"] = float((~torch.isnan(p3d[:, 0])).double().mean().item())
 
-    # ---- e2e: host buffers through the C-ABI host pipeline (H2D + kernel + D2H per step) ----
+    # ---- e2e: host buffers through the C-ABI host pipeline (H2D + kernel + D2H per step), every
+    # rank streams its own shard concurrently ----
     n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else N
     e2e = None
     try:
@@ -371,20 +376,32 @@ def run_gpu(args):
         e2e_step()
         torch.cuda.synchronize()
         ke = max(1, min(args.steps, 5))
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
             e2e_step()
         dt = (time.perf_counter() - t0) / ke
+        if world > 1:
+            td = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            dt = float(td.item())
         # the pipeline's output equals the resident run
         assert torch.equal(h_p3d.nan_to_num(), p3d[:n_e2e].cpu().nan_to_num())
         d2h = n_e2e * 32 + (n_e2e * C * 17 if args.workload == "ransac" else 0)
-        e2e = {"value": n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 16,
-               "d2h_bytes_per_step": d2h, "joint_instances": n_e2e, "ms_per_step": dt * 1e3,
+        e2e = {"value": world * n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 16,
+               "d2h_bytes_per_step": d2h, "joint_instances_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
                "api": "m3d_triangulate_%s_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"
-                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": 1}
+                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": world}
         del h_xy, h_p3d, h_err
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- CPU baseline: loop-faithful port, one core, bounded sample ---------------------------
     cpu = None
