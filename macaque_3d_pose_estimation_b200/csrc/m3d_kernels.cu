@@ -577,10 +577,11 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
   const int64_t blocks = (N + per_block - 1) / per_block;
   if (blocks > 0x7fffffffLL) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: N too large for one launch");
   const int C = rig->dev.n_cams;
-  const size_t smem = ransac_smem_bytes(C > 0 ? C : 1);
-#define CALLV(F, P, NC, MB)                                                                        \
+  const int GSv = C <= 8 ? 8 : 16;
+  const size_t smem = ransac_smem_bytes(C > 0 ? C : 1, GSv);
+#define CALLV(F, P, NC, GSZ, MB)                                                                   \
   do {                                                                                             \
-    auto kfn = k_ransac<F, P, NC, MB>;                                                             \
+    auto kfn = k_ransac<F, P, NC, GSZ, MB>;                                                          \
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     kfn<<<(unsigned)blocks, RANSAC_THREADS, smem, st>>>(rig->dev, rig->dev_g, xy, N, undistort, min_cams, \
                                                         threshold, init_best, p3d, picked, xy_picked, err, \
@@ -588,8 +589,9 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
   } while (0)
 #define CALL(F, P)                                          \
   do {                                                      \
-    if (C == 8) CALLV(F, P, 8, 4);                          \
-    else CALLV(F, P, 0, 4);                                 \
+    if (C == 8) CALLV(F, P, 8, 8, 4);                       \
+    else if (C < 8) CALLV(F, P, 0, 8, 4);                   \
+    else CALLV(F, P, 0, 16, 4);                             \
   } while (0)
   M3D_DISPATCH_MODEL(rig, CALL);
 #undef CALL
