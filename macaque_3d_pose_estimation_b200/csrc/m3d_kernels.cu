@@ -50,6 +50,10 @@ struct m3d_rig {
   RigDev dev;
   RigDev* dev_g = nullptr;  // device-resident copy (kernels that index cameras per lane)
   int device;
+  // stream-ordered scratch of the RANSAC launches comes from a private pool that keeps its
+  // memory between launches (the default pool trims at every synchronisation)
+  cudaMemPool_t pool = nullptr;
+  std::mutex pool_mutex;
   // workspace of the *_host pipelines (lazily allocated, guarded by ws_mutex)
   std::mutex ws_mutex;
   static const int kSlots = 3;
@@ -413,6 +417,7 @@ void m3d_rig_destroy(m3d_rig* rig) {
     DeviceGuard g(rig->device);
     free_workspace(rig);
     cudaFree(rig->dev_g);
+    if (rig->pool) cudaMemPoolDestroy(rig->pool);
   }
   delete rig;
 }
@@ -569,34 +574,92 @@ int m3d_reproj_error(const m3d_rig* rig, const double* p3d, const double* xy, in
   return check_launch("k_reproj");
 }
 
+// joint-instances per internal ransac launch: bounds the scratch (undistorted views + slots,
+// 16 C + 64 bytes per instance) to ~0.8 GB at C = 8
+static const int64_t kRansacChunk = 1 << 22;
+
 static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int undistort, int min_cams,
                          double threshold, double init_best, double* p3d, uint8_t* picked,
                          double* xy_picked, double* err, int32_t* subset, int32_t* neval,
                          cudaStream_t st) {
-  const int64_t per_block = RANSAC_THREADS;
-  const int64_t blocks = (N + per_block - 1) / per_block;
-  if (blocks > 0x7fffffffLL) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: N too large for one launch");
   const int C = rig->dev.n_cams;
+  const int sms = sm_count_of(rig->device);
   const int GSv = C <= 8 ? 8 : 16;
   const size_t smem = ransac_smem_bytes(C > 0 ? C : 1, GSv);
-#define CALLV(F, P, NC, GSZ, MB)                                                                   \
-  do {                                                                                             \
-    auto kfn = k_ransac<F, P, NC, GSZ, MB>;                                                          \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem, st>>>(rig->dev, rig->dev_g, xy, N, undistort, min_cams, \
-                                                        threshold, init_best, p3d, picked, xy_picked, err, \
-                                                        subset, neval);                                    \
+  const int64_t chunk = N < kRansacChunk ? N : kRansacChunk;
+  double* U = nullptr;
+  RansacSlot* slots = nullptr;
+  unsigned long long* counter = nullptr;
+  {
+    m3d_rig* mrig = const_cast<m3d_rig*>(rig);
+    std::lock_guard<std::mutex> lock(mrig->pool_mutex);
+    if (!mrig->pool) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = rig->device;
+      M3D_CUDA(cudaMemPoolCreate(&mrig->pool, &props));
+      unsigned long long keep = ~0ull;
+      M3D_CUDA(cudaMemPoolSetAttribute(mrig->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+  }
+  M3D_CUDA(cudaMallocFromPoolAsync(&U, sizeof(double) * 2 * (size_t)(C > 0 ? C : 1) * chunk, rig->pool, st));
+  M3D_CUDA(cudaMallocFromPoolAsync(&slots, sizeof(RansacSlot) * (size_t)chunk, rig->pool, st));
+  M3D_CUDA(cudaMallocFromPoolAsync(&counter, sizeof(unsigned long long), rig->pool, st));
+  int rc = M3D_OK;
+  for (int64_t n0 = 0; n0 < N && rc == M3D_OK; n0 += chunk) {
+    const int64_t n = (N - n0) < chunk ? (N - n0) : chunk;
+    const int gridA = grid_for(n, 256, sms);
+#define CALLA(F, P, NC) \
+  k_ransac_full<F, P, NC><<<gridA, 256, 0, st>>>(rig->dev, xy, N, n0, n, undistort, min_cams, threshold, init_best, U, slots)
+#define CALL(F, P)                   \
+  do {                               \
+    if (C == 8) CALLA(F, P, 8);      \
+    else CALLA(F, P, 0);             \
   } while (0)
-#define CALL(F, P)                                          \
-  do {                                                      \
-    if (C == 8) CALLV(F, P, 8, 8, 4);                       \
-    else if (C < 8) CALLV(F, P, 0, 8, 4);                   \
-    else CALLV(F, P, 0, 16, 4);                             \
-  } while (0)
-  M3D_DISPATCH_MODEL(rig, CALL);
+    M3D_DISPATCH_MODEL(rig, CALL);
 #undef CALL
-#undef CALLV
-  return check_launch("k_ransac");
+#undef CALLA
+    rc = check_launch("k_ransac_full");
+    if (rc) break;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) {
+      rc = fail(M3D_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+      break;
+    }
+#define CALLB(F, P, GSZ, MB)                                                                              \
+  do {                                                                                                    \
+    auto kfn = k_ransac_search<F, P, GSZ, MB>;                                                            \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    int per_sm = 0;                                                                                       \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RANSAC_THREADS, smem);                    \
+    if (per_sm < 1) per_sm = 1;                                                                           \
+    int64_t blocks = (int64_t)sms * per_sm;                                                               \
+    const int64_t need = (n + 32 * RANSAC_WARPS - 1) / (32 * RANSAC_WARPS);                               \
+    if (blocks > need) blocks = need;                                                                     \
+    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,    \
+                                                        init_best, U, slots, counter);                    \
+  } while (0)
+    // measured on B200: 128 registers (4 CTAs / SM) beats every tighter cap (spills) and a
+    // larger shared-memory carve-out (smaller L1 for the spill traffic)
+#define CALL(F, P)                          \
+  do {                                      \
+    if (C <= 8) CALLB(F, P, 8, 4);          \
+    else CALLB(F, P, 16, 4);                \
+  } while (0)
+    M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+#undef CALLB
+    rc = check_launch("k_ransac_search");
+    if (rc) break;
+    k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
+                                                         subset, neval);
+    rc = check_launch("k_ransac_emit");
+  }
+  cudaFreeAsync(U, st);
+  cudaFreeAsync(slots, st);
+  cudaFreeAsync(counter, st);
+  return rc;
 }
 
 int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,

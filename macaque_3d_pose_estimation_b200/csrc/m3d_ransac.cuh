@@ -1,5 +1,5 @@
 // m3d_ransac.cuh — K4: camera-subset RANSAC, i.e. CameraGroup.triangulate_possible with one
-// candidate per camera (cameras.py:639-743), as one fused kernel.
+// candidate per camera (cameras.py:639-743).
 //
 // Semantics: visit the subsets of the k valid cameras in
 // itertools.product order (step s drops camera V[j] iff bit k-1-j of s is set), skip the
@@ -8,20 +8,26 @@
 //   T1 = min(thr, init_best);  s* = first admissible s with err(s) < T1 if one exists,
 //   else the strict arg-min of err over admissible s (first on ties) if below init_best.
 //
-// Schedule
-//   phase A  lane = point: undistort every view once (kept in shared memory), solve the
-//            full set (s = 0), rank the cameras by their residual at that solution
-//            ("suspicion order").  ~20 % of the points finish here.
-//   phase B  a GROUP of GS lanes (8 for rigs of up to 8 cameras) = one point, lane = subset
-//            (GS consecutive s per step), 32 / GS points in flight per warp; a group that
-//            finishes its point takes the next unfinished one of the warp's tile.  Per step
-//            every lane sums the per-camera Gram blocks of its subset (low log2(GS) cameras
-//            pre-summed per lane, the rest group-uniform) and solves; then ONE projection on
-//            the subset's most suspicious camera prunes every subset whose residual already
-//            exceeds T * |S| (exact: the mean cannot come back under T).  The few survivors
-//            are scored cooperatively — lane = camera, fixed butterfly sum — in ascending
-//            s, which keeps the sequential accept / stop rule of the reference.  Pass 2 (no
-//            subset under T1, rare) repeats the scan with the running best as T.
+// Three kernels per launch (per-point cost varies by two orders of magnitude, so the
+// search itself runs on persistent warps that pull work from a global counter):
+//   k_ransac_full   thread = point.  Undistort every view once (written to scratch, camera
+//                   planes, coalesced), solve the full set (s = 0), rank the cameras by
+//                   their residual there ("suspicion order"), write the per-point slot.
+//                   ~20 % of the points are decided here.
+//   k_ransac_search persistent warps; a GROUP of GS lanes (8 for rigs of up to 8 cameras) =
+//                   one point, lane = subset (GS consecutive s per step), 32 / GS points in
+//                   flight per warp; idle groups take the next undecided point of the
+//                   warp's current 32-point batch, batches come from an atomic counter.
+//                   Per step every lane sums the per-camera Gram blocks of its subset (low
+//                   log2(GS) cameras pre-summed per lane, the rest group-uniform) and
+//                   solves; then ONE projection on the subset's most suspicious camera
+//                   prunes every subset whose residual already exceeds T * |S| (exact: the
+//                   mean cannot come back under T).  The few survivors are scored
+//                   cooperatively — lane = camera, fixed butterfly sum — in ascending s,
+//                   which keeps the sequential accept / stop rule of the reference.
+//                   Pass 2 (no subset under T1, rare) rescans with the running best as T.
+//   k_ransac_emit   thread = point.  Expands the slots into the reference's outputs
+//                   (p3d, errors, picked, points_2d, ...), every plane coalesced.
 // Every pruning decision is made on converged fp64 values, so the selected subset is the
 // reference's unless an error lands within ~1e-10 px of a threshold (LAPACK's own noise).
 #pragma once
@@ -35,24 +41,26 @@ constexpr int RANSAC_THREADS = RANSAC_WARPS * 32;
 
 __host__ __device__ inline size_t ransac_rig_bytes() { return (sizeof(RigDev) + 15) & ~size_t(15); }
 
-// per-point record shared between phase A (lane = point) and phase B (group = point)
+// per-point record handed from k_ransac_full to k_ransac_search to k_ransac_emit
 struct RansacSlot {
   double best_err, bx, by, bz;
-  unsigned long long ord;
+  unsigned long long ord;  // cameras by decreasing residual at the full-set solution, 4 bits each
   uint32_t vmask, umask, best_mask;
-  int32_t best_s, neval, pad;
+  int32_t best_s, neval;
+  int32_t decided;  // 1: nothing left to search
 };
 static_assert(sizeof(RansacSlot) == 64, "RansacSlot layout");
 
-// per warp: U[C][32] double2 | slots[32] | per group (32/GS of them): raw[C][2] | gc[C] | glow[10][GS]
+// shared memory of k_ransac_search: rig | per warp, per group: raw[C][2] | gc[C] | glow[10][GS]
+// (+64 B so that consecutive groups start 16 banks apart: a 64-bit access of 4 groups x 8
+// lanes then takes the minimum two wavefronts)
 __host__ __device__ inline size_t ransac_group_bytes(int C, int GS) {
-  return (size_t)C * 16 + (size_t)C * sizeof(Gram) + (size_t)10 * GS * 8;
-}
-__host__ __device__ inline size_t ransac_warp_bytes(int C, int GS) {
-  return (size_t)C * 32 * 16 + 32 * sizeof(RansacSlot) + (size_t)(32 / GS) * ransac_group_bytes(C, GS);
+  size_t b = (size_t)C * 16 + (size_t)C * sizeof(Gram) + (size_t)10 * GS * 8;
+  b = (b + 127) & ~size_t(127);
+  return b + 64;
 }
 inline size_t ransac_smem_bytes(int C, int GS) {
-  return ransac_rig_bytes() + RANSAC_WARPS * ransac_warp_bytes(C, GS);
+  return ransac_rig_bytes() + (size_t)RANSAC_WARPS * (32 / GS) * ransac_group_bytes(C, GS);
 }
 
 // next camera of subset cm in suspicion order, starting at position pos (returns -1 when the
@@ -66,60 +74,30 @@ __device__ __forceinline__ int next_member(unsigned long long ord, int C, uint32
   return -1;
 }
 
-template <bool FULL, bool PO, int NC, int GS, int MINB>
-__global__ void __launch_bounds__(RANSAC_THREADS, MINB)
-k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
-         const double* __restrict__ xy, int64_t N, int undistort, int min_cams, double thr,
-         double init_best, double* __restrict__ p3d, uint8_t* __restrict__ picked,
-         double* __restrict__ xy_picked, double* __restrict__ err_out,
-         int32_t* __restrict__ subset_out, int32_t* __restrict__ neval_out) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  constexpr unsigned FULLM = 0xffffffffu;
-  constexpr int NG = 32 / GS;            // points in flight per warp
-  constexpr int LOGGS = GS == 8 ? 3 : (GS == 16 ? 4 : 5);
+// ---------------------------------------------------------------------------------------
+// full-set pass: thread = point
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO, int NC>
+__global__ void __launch_bounds__(256, 2)
+k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t ld, int64_t n0,
+              int64_t n, int undistort, int min_cams, double thr, double init_best,
+              double* __restrict__ U, RansacSlot* __restrict__ slots) {
+  // xy: (C, ld, 2) planes, this launch covers points [n0, n0 + n); U: (C, n, 2); slots: (n)
   const int C = NC > 0 ? NC : rig.n_cams;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / GS, j = lane % GS;  // group and lane-in-group
-  const int gshift = g * GS;
-  constexpr uint32_t GM = GS == 32 ? 0xffffffffu : ((1u << GS) - 1u);
-  RigDev& srig = *reinterpret_cast<RigDev*>(smem);
-  unsigned char* wbase = smem + ransac_rig_bytes() + (size_t)warp * ransac_warp_bytes(C, GS);
-  double2* Us = reinterpret_cast<double2*>(wbase);                              // [C][32] undistorted
-  RansacSlot* slots = reinterpret_cast<RansacSlot*>(wbase + (size_t)C * 512);   // [32]
-  unsigned char* gbase = wbase + (size_t)C * 512 + 32 * sizeof(RansacSlot) + (size_t)g * ransac_group_bytes(C, GS);
-  double* raws = reinterpret_cast<double*>(gbase);                              // [C][2] raw, group's point
-  Gram* gcs = reinterpret_cast<Gram*>(gbase + (size_t)C * 16);                  // [C]
-  double* glow = reinterpret_cast<double*>(gbase + (size_t)C * 16 + (size_t)C * sizeof(Gram));  // [10][GS]
-
-  // rig copy for per-lane camera indexing (constant-bank reads with lane-varying addresses
-  // would serialise)
-  {
-    const double* src = reinterpret_cast<const double*>(rig_g);
-    double* dst = reinterpret_cast<double*>(&srig);
-    for (int i = threadIdx.x; i < (int)(sizeof(RigDev) / 8); i += RANSAC_THREADS) dst[i] = src[i];
-  }
-  __syncthreads();
-
-  const int64_t tile0 = ((int64_t)blockIdx.x * RANSAC_WARPS + warp) * 32;
-  if (tile0 >= N) return;
-  const int64_t n = tile0 + lane;
-  const bool inb = n < N;
-  const double T1 = thr < init_best ? thr : init_best;
-
-  // ---- phase A ---------------------------------------------------------------------------
-  uint32_t vmask = 0, umask = 0;
-  unsigned long long ord = 0;
-  double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
-  int32_t best_s = -1, neval = 0;
-  uint32_t best_mask = 0;
-  bool done = !inb;
-  if (NC > 0) {
-    double2 raw[NC > 0 ? NC : 1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t vmask = 0, umask = 0;
+    unsigned long long ord = 0;
+    double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
+    int32_t best_s = -1;
+    uint32_t best_mask = 0;
+    bool done = false;
     Gram G;
     gram_zero(G);
-    if (inb) {
+    if (NC > 0) {
+      double2 raw[NC > 0 ? NC : 1];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) raw[c] = ld_xy(xy, (int64_t)c * N + n);
+      for (int c = 0; c < NC; ++c) raw[c] = ld_xy(xy, (int64_t)c * ld + n0 + i);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         double x = raw[c].x, y = raw[c].y;
@@ -131,9 +109,8 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
             gram_add_camera(G, rig.cam[c], x, y);
           }
         }
-        Us[c * 32 + lane] = make_double2(x, y);
+        st_xy(U, (int64_t)c * n + i, x, y);
       }
-      neval = 1;  // the full set is always tried (cameras.py:691)
       unsigned long long key[NC > 0 ? NC : 1];
 #pragma unroll
       for (int c = 0; c < NC; ++c) key[c] = (unsigned long long)c;
@@ -168,37 +145,29 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
           if (e0 < thr) done = true;
         }
       }
-      const int k = __popc(vmask);
-      if (k < 2 || k <= min_cams) done = true;  // every smaller subset would be skipped
-      if (!done) {
-        // Batcher odd-even merge sort, descending
-#define M3D_CE(a, b)                         \
-  {                                          \
+      // Batcher odd-even merge sort of the 8 keys, descending
+#define M3D_CE(a, b)                                                   \
+  {                                                                    \
     const unsigned long long lo__ = key[a] < key[b] ? key[a] : key[b]; \
     const unsigned long long hi__ = key[a] < key[b] ? key[b] : key[a]; \
-    key[a] = hi__;                           \
-    key[b] = lo__;                           \
+    key[a] = hi__;                                                     \
+    key[b] = lo__;                                                     \
   }
-        if (NC == 8) {
-          M3D_CE(0, 1) M3D_CE(2, 3) M3D_CE(4, 5) M3D_CE(6, 7)
-          M3D_CE(0, 2) M3D_CE(1, 3) M3D_CE(4, 6) M3D_CE(5, 7)
-          M3D_CE(1, 2) M3D_CE(5, 6)
-          M3D_CE(0, 4) M3D_CE(1, 5) M3D_CE(2, 6) M3D_CE(3, 7)
-          M3D_CE(2, 4) M3D_CE(3, 5)
-          M3D_CE(1, 2) M3D_CE(3, 4) M3D_CE(5, 6)
-        }
+      if (NC == 8) {
+        M3D_CE(0, 1) M3D_CE(2, 3) M3D_CE(4, 5) M3D_CE(6, 7)
+        M3D_CE(0, 2) M3D_CE(1, 3) M3D_CE(4, 6) M3D_CE(5, 7)
+        M3D_CE(1, 2) M3D_CE(5, 6)
+        M3D_CE(0, 4) M3D_CE(1, 5) M3D_CE(2, 6) M3D_CE(3, 7)
+        M3D_CE(2, 4) M3D_CE(3, 5)
+        M3D_CE(1, 2) M3D_CE(3, 4) M3D_CE(5, 6)
+      }
 #undef M3D_CE
 #pragma unroll
-        for (int i = 0; i < NC; ++i) ord |= (key[i] & 15ull) << (4 * i);
-      }
-    }
-  } else {
-    if (inb) {
-      Gram G;
-      gram_zero(G);
+      for (int c = 0; c < NC; ++c) ord |= (key[c] & 15ull) << (4 * c);
+    } else {
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
-        const double2 p = ld_xy(xy, (int64_t)c * N + n);
+        const double2 p = ld_xy(xy, (int64_t)c * ld + n0 + i);
         double x = p.x, y = p.y;
         if (p.x == p.x) {
           vmask |= 1u << c;
@@ -208,10 +177,9 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
             gram_add_camera(G, rig.cam[c], x, y);
           }
         }
-        Us[c * 32 + lane] = make_double2(x, y);
+        st_xy(U, (int64_t)c * n + i, x, y);
         ord |= (unsigned long long)c << (4 * c);  // identity order
       }
-      neval = 1;
       if (__popc(umask) >= 2) {
         double X, Y, Z;
         dlt_solve(G, X, Y, Z);
@@ -219,7 +187,7 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
         int m = 0;
         for (uint32_t rest = vmask; rest; rest &= rest - 1) {
           const int c = __ffs(rest) - 1;
-          const double2 p = ld_xy(xy, (int64_t)c * N + n);
+          const double2 p = ld_xy(xy, (int64_t)c * ld + n0 + i);
           double u, v;
           project_point<FULL, PO>(rig.cam[c], X, Y, Z, u, v);
           const double e = residual_norm(p.x - u, p.y - v);
@@ -239,11 +207,9 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
           if (e0 < thr) done = true;
         }
       }
-      const int k = __popc(vmask);
-      if (k < 2 || k <= min_cams) done = true;
     }
-  }
-  {
+    const int k = __popc(vmask);
+    if (k < 2 || k <= min_cams) done = true;  // every smaller subset would be skipped
     RansacSlot sl;
     sl.best_err = best_err;
     sl.bx = bx;
@@ -254,33 +220,81 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
     sl.umask = umask;
     sl.best_mask = best_mask;
     sl.best_s = best_s;
-    sl.neval = neval;
-    sl.pad = 0;
-    slots[lane] = sl;
+    sl.neval = 1;  // the full set is always tried (cameras.py:691)
+    sl.decided = done ? 1 : 0;
+    slots[i] = sl;
   }
-  __syncwarp();
+}
 
-  // ---- phase B ---------------------------------------------------------------------------
-  uint32_t todo = __ballot_sync(FULLM, !done);
+// ---------------------------------------------------------------------------------------
+// subset search: persistent warps, group of GS lanes = point, lane = subset
+// ---------------------------------------------------------------------------------------
+template <bool FULL, bool PO, int GS, int MINB>
+__global__ void __launch_bounds__(RANSAC_THREADS, MINB)
+k_ransac_search(const RigDev* __restrict__ rig_g, const double* __restrict__ xy, int64_t ld, int64_t n0,
+                int64_t n, int min_cams, double thr, double init_best, const double* __restrict__ U,
+                RansacSlot* __restrict__ slots, unsigned long long* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr unsigned FULLM = 0xffffffffu;
+  constexpr int NG = 32 / GS;  // points in flight per warp
+  constexpr int LOGGS = GS == 8 ? 3 : (GS == 16 ? 4 : 5);
+  constexpr uint32_t GM = GS == 32 ? 0xffffffffu : ((1u << GS) - 1u);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / GS, j = lane % GS;  // group and lane-in-group
+  const int gshift = g * GS;
+  RigDev& srig = *reinterpret_cast<RigDev*>(smem);
+  {
+    // rig copy for per-lane camera indexing (constant-bank reads with lane-varying addresses
+    // would serialise)
+    const double* src = reinterpret_cast<const double*>(rig_g);
+    double* dst = reinterpret_cast<double*>(&srig);
+    for (int i = threadIdx.x; i < (int)(sizeof(RigDev) / 8); i += RANSAC_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int C = srig.n_cams;
+  unsigned char* gbase = smem + ransac_rig_bytes() + (size_t)(warp * NG + g) * ransac_group_bytes(C, GS);
+  double* raws = reinterpret_cast<double*>(gbase);                              // [C][2] raw pixels
+  Gram* gcs = reinterpret_cast<Gram*>(gbase + (size_t)C * 16);                  // [C] Gram blocks
+  double* glow = reinterpret_cast<double*>(gbase + (size_t)C * 16 + (size_t)C * sizeof(Gram));  // [10][GS]
+  const double T1 = thr < init_best ? thr : init_best;
+
+  uint32_t todo = 0;      // undecided points of the current batch
+  int64_t batch0 = 0;     // first point of the current batch
+  bool exhausted = false;
   // group state, replicated in the lanes of the group
-  int cur = -1;            // point (lane index in the tile) the group works on
+  int64_t cur = -1;       // point the group works on
   bool fresh = false;
   uint32_t vm = 0, um = 0, vhigh = 0, cm_low = 0, base = 0, n_sub = 0;
-  unsigned long long ordp = 0;
+  unsigned long long ordp = 0, hcam = 0;  // hcam: nibble b = camera dropped by bit b of s >> log2(GS)
   int k = 0, khigh = 0, pass = 1;
   int32_t ne = 0;
   double rb = T1;
 #pragma unroll 1
   for (;;) {
-    // hand unfinished points to idle groups (warp-uniform)
+    // hand undecided points to idle groups; fetch a new batch of 32 points when the current
+    // one is used up (warp-uniform)
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
-      const int cg = __shfl_sync(FULLM, cur, gi * GS);
-      if (cg < 0 && todo) {
+      const bool idle = __shfl_sync(FULLM, cur < 0 ? 1 : 0, gi * GS) != 0;
+      if (!idle) continue;
+      while (!todo && !exhausted) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(counter, 32ull);
+        b = __shfl_sync(FULLM, b, 0);
+        if ((int64_t)b >= n) {
+          exhausted = true;
+        } else {
+          batch0 = (int64_t)b;
+          const int64_t i = batch0 + lane;
+          const bool open = (i < n) && (slots[i].decided == 0);
+          todo = __ballot_sync(FULLM, open);
+        }
+      }
+      if (todo) {
         const int p = __ffs(todo) - 1;
         todo &= todo - 1;
         if (g == gi) {
-          cur = p;
+          cur = batch0 + p;
           fresh = true;
         }
       }
@@ -288,20 +302,20 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
     if (!__any_sync(FULLM, cur >= 0)) break;
     if (__any_sync(FULLM, fresh)) {
       if (fresh) {
-        const RansacSlot& sl = slots[cur];
-        vm = sl.vmask;
-        um = sl.umask;
-        ordp = sl.ord;
+        const RansacSlot* sl = slots + cur;
+        vm = sl->vmask;
+        um = sl->umask;
+        ordp = sl->ord;
         k = __popc(vm);
         n_sub = 1u << k;
         if (j < C) {  // lane = camera: raw pixels and Gram block of the group's point
-          const double2 q = ld_xy(xy, (int64_t)j * N + tile0 + cur);
+          const double2 q = ld_xy(xy, (int64_t)j * ld + n0 + cur);
           raws[2 * j] = q.x;
           raws[2 * j + 1] = q.y;
           Gram gg;
           gram_zero(gg);
           if ((um >> j) & 1u) {
-            const double2 u = Us[j * 32 + cur];
+            const double2 u = ld_xy(U, (int64_t)j * n + cur);
             gram_add_camera(gg, srig.cam[j], u.x, u.y);
           }
           gcs[j] = gg;
@@ -316,6 +330,12 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
         for (int i = 0; i < k - klow; ++i) vlow &= vlow - 1;
         vhigh = vm & ~vlow;
         khigh = k - klow;
+        hcam = 0;
+        {
+          int jj = 0;  // V[jj] (ascending) is dropped by bit khigh-1-jj
+          for (uint32_t rest = vhigh; rest; rest &= rest - 1, ++jj)
+            hcam |= (unsigned long long)(__ffs(rest) - 1) << (4 * (khigh - 1 - jj));
+        }
         cm_low = subset_mask(vlow, klow, (uint32_t)j & ((1u << klow) - 1u));
         Gram gg;
         gram_zero(gg);
@@ -341,7 +361,10 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
     uint32_t cm = 0;
     bool adm = false;
     if (act && s >= 1 && s < n_sub) {
-      cm = subset_mask(vhigh, khigh, base >> LOGGS) | cm_low;
+      uint32_t dropped = 0;
+      for (uint32_t h = base >> LOGGS, b = 0; h; h >>= 1, ++b)
+        if (h & 1u) dropped |= 1u << (uint32_t)((hcam >> (4 * b)) & 15ull);
+      cm = (vhigh & ~dropped) | cm_low;
       const int cnt = __popc(cm);
       adm = (cnt >= min_cams) || (cnt == k);
     }
@@ -396,13 +419,13 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
       const double el = (m >= 2) ? sum / (double)m : qnan();
       if (has && el < rb) {
         if (j == 0) {
-          RansacSlot& sl = slots[cur];
-          sl.best_err = el;
-          sl.best_s = (int32_t)(base + l);
-          sl.best_mask = cml;
-          sl.bx = Xl;
-          sl.by = Yl;
-          sl.bz = Zl;
+          RansacSlot* sl = slots + cur;
+          sl->best_err = el;
+          sl->best_s = (int32_t)(base + l);
+          sl->best_mask = cml;
+          sl->bx = Xl;
+          sl->by = Yl;
+          sl->bz = Zl;
         }
         if (pass == 1) {
           // first subset under T1: the reference stops here; later subsets of this step were
@@ -421,7 +444,7 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
         if (pass == 1) {  // nothing under T1: rescan for the strict arg-min
           pass = 2;
           base = 0;
-          rb = slots[cur].best_err;
+          rb = slots[cur].best_err;  // init_best or the full-set error (>= T1)
         } else {
           finished = true;
         }
@@ -433,26 +456,35 @@ k_ransac(const __grid_constant__ RigDev rig, const RigDev* __restrict__ rig_g,
     }
     __syncwarp();
   }
-  __syncwarp();
+}
 
-  // ---- outputs: lane = point again, coalesced per plane ---------------------------------------
-  if (inb) {
-    const RansacSlot sl = slots[lane];
-    p3d[3 * n] = sl.bx;
-    p3d[3 * n + 1] = sl.by;
-    p3d[3 * n + 2] = sl.bz;
-    err_out[n] = (sl.best_s >= 0) ? sl.best_err : 0.0;  // errors default to 0.0 (cameras.py:675)
-    if (subset_out) subset_out[n] = sl.best_s;
-    if (neval_out) neval_out[n] = sl.neval;
+// ---------------------------------------------------------------------------------------
+// outputs: thread = point, every plane coalesced
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ransac_emit(int C, const double* __restrict__ xy, int64_t ld, int64_t n0, int64_t n,
+              const RansacSlot* __restrict__ slots, double* __restrict__ p3d, uint8_t* __restrict__ picked,
+              double* __restrict__ xy_picked, double* __restrict__ err_out,
+              int32_t* __restrict__ subset_out, int32_t* __restrict__ neval_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const RansacSlot sl = slots[i];
+    const int64_t o = n0 + i;
+    p3d[3 * o] = sl.bx;
+    p3d[3 * o + 1] = sl.by;
+    p3d[3 * o + 2] = sl.bz;
+    err_out[o] = (sl.best_s >= 0) ? sl.best_err : 0.0;  // errors default to 0.0 (cameras.py:675)
+    if (subset_out) subset_out[o] = sl.best_s;
+    if (neval_out) neval_out[o] = sl.neval;
     if (picked || xy_picked) {
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
         const bool in = (sl.best_mask >> c) & 1u;
-        if (picked) picked[(int64_t)c * N + n] = in ? 1 : 0;
+        if (picked) picked[(int64_t)c * ld + o] = in ? 1 : 0;
         if (xy_picked) {
           double2 q = make_double2(qnan(), qnan());
-          if (in) q = ld_xy(xy, (int64_t)c * N + n);
-          st_xy(xy_picked, (int64_t)c * N + n, q.x, q.y);
+          if (in) q = ld_xy(xy, (int64_t)c * ld + o);
+          st_xy(xy_picked, (int64_t)c * ld + o, q.x, q.y);
         }
       }
     }
