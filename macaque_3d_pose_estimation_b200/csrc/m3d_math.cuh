@@ -472,17 +472,23 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
     const double det = a * c00 + b * c01 + c * c02;
     // positive definite (Sylvester) <=> lam < lam_min(H): we are on the right branch
     if (!(a > 0.0 && c22 > 0.0 && det > 0.0)) break;
-    const double idet = rcp(det);
-    x0 = -(c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2]) * idet;
-    x1 = -(c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2]) * idet;
-    x2 = -(c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2]) * idet;
-    const double fl = G.w - lam + (G.g[0] * x0 + G.g[1] * x1 + G.g[2] * x2);
-    const double n2 = 1.0 + x0 * x0 + x1 * x1 + x2 * x2;
-    const double dl = fl * rcp(n2);
+    // p = adj(H - lam I) g = -det X.  The Newton step f / (1 + |X|^2) needs one reciprocal
+    // in this form (and no 1/det on the dependency chain):
+    //   f = w - lam - (g.p)/det ,  1 + |X|^2 = (det^2 + |p|^2)/det^2
+    const double p0 = c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2];
+    const double p1 = c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2];
+    const double p2 = c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2];
+    const double q = G.g[0] * p0 + G.g[1] * p1 + G.g[2] * p2;
+    const double pp = p0 * p0 + p1 * p1 + p2 * p2;
+    const double dl = det * ((G.w - lam) * det - q) * rcp(det * det + pp);
     // lam_min(H - lam I) >= det / tr^2 ; a step below 1e-7 of that changes X by < 1e-14 |X|
     // beyond the first-order correction applied here.
     const double mu_lb = det * itr2;
     if (fabs(dl) <= 1e-7 * mu_lb) {
+      const double idet = rcp(det);
+      x0 = -p0 * idet;
+      x1 = -p1 * idet;
+      x2 = -p2 * idet;
       // first-order update X(lam + dl) = X + dl (H - lam I)^-1 X
       const double y0 = (c00 * x0 + c01 * x1 + c02 * x2) * idet;
       const double y1 = (c01 * x0 + c11 * x1 + c12 * x2) * idet;

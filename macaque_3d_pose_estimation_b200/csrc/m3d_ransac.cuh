@@ -14,7 +14,7 @@
 //                   planes, coalesced), solve the full set (s = 0), rank the cameras by
 //                   their residual there ("suspicion order"), write the per-point slot.
 //                   ~20 % of the points are decided here.
-//   k_ransac_search persistent warps; a GROUP of GS lanes (8 for rigs of up to 8 cameras) =
+//   k_ransac_search persistent warps; a GROUP of GS = 16 lanes (>= cameras) =
 //                   one point, lane = subset (GS consecutive s per step), 32 / GS points in
 //                   flight per warp; idle groups take the next undecided point of the
 //                   warp's current 32-point batch, batches come from an atomic counter.
