@@ -258,3 +258,34 @@ def test_gpu_step4_stage_matches_oracle():
             assert np.array_equal(res["kp3d_score"][a], s3, equal_nan=True)
             assert _eq_nan(res["kp3d_err"][a], e3)
             assert np.nanmax(np.abs(res["kp3d_err"][a] - e3)) <= ERR_TOL_PX
+
+
+def test_gpu_distort_points_and_camera_models():
+    """Camera.distort_points (cameras.py:301,366,487) = projectPoints of (x, y, 1) with identity
+    extrinsics, for the three camera models, against the oracle."""
+    from oracle import camera_math as cm
+    rng = np.random.default_rng(5)
+    xy = rng.uniform(-0.6, 0.6, size=(500, 2))
+    xyz = np.concatenate([xy, np.ones((500, 1))], axis=1)
+    for model in ("pinhole", "pinhole8", "fisheye", "omnidir"):
+        d = synth.make_rig(1, model, seed=21)[0]
+        cg = CameraGroup.from_dicts([d])
+        cam = cg.cameras[0]
+        spec = fixtures.cams_from_dicts([d])[0]
+        z3 = np.zeros(3)
+        if spec.model == cm.MODEL_PINHOLE:
+            ref = cm.project_pinhole(xyz, z3, z3, spec.K, spec.dist)
+        elif spec.model == cm.MODEL_FISHEYE:
+            ref = cm.project_fisheye(xyz, z3, z3, spec.K, spec.dist)
+        else:
+            ref = cm.project_omnidir(xyz, z3, z3, spec.K, spec.xi, spec.dist)
+        out = cam.distort_points(xy)
+        assert out.shape == xy.shape and np.abs(out - ref).max() <= 1e-9
+        # undistort(distort(x)) comes back to x up to the model's fixed iteration count
+        back = cam.undistort_points(out)
+        tol = 5e-3 if model.startswith("pinhole") else 1e-7
+        assert np.abs(back - xy).max() <= tol
+        # per-camera reprojection_error = p2d - project(p3d) (cameras.py:325-327)
+        X = synth.make_tracks(5, 2, seed=3).reshape(-1, 3)
+        p2 = spec.project(X) + 1.0
+        assert np.abs(cam.reprojection_error(X, p2) - 1.0).max() <= 1e-9
