@@ -106,21 +106,27 @@ def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, devi
     g.manual_seed(seed)
     f64 = torch.float64
     root0 = torch.rand((n_animals, 3), generator=g, device=device, dtype=f64)
-    lo = torch.tensor([-900.0, -900.0, 0.0], device=device, dtype=f64)
-    hi = torch.tensor([900.0, 900.0, 1500.0], device=device, dtype=f64)
+    # animal roots stay inside the volume every camera of the ring rig sees (the cage centre)
+    lo = torch.tensor([-600.0, -600.0, 0.0], device=device, dtype=f64)
+    hi = torch.tensor([600.0, 600.0, 800.0], device=device, dtype=f64)
     root0 = lo + root0 * (hi - lo)
     steps = torch.randn((n_frames, n_animals, 3), generator=g, device=device, dtype=f64) * 15.0
     root = root0[None] + torch.cumsum(steps, dim=0)
     del steps
     # keep the animals in the cage: reflect the walk into the box
-    span = hi - lo + 200.0
-    root = lo - 100.0 + (span - ((root - lo + 100.0) % (2 * span) - span).abs()).abs()
+    span = hi - lo
+    root = lo + (span - ((root - lo) % (2 * span) - span).abs()).abs()
     skel = torch.randn((n_animals, n_joints, 3), generator=g, device=device, dtype=f64) * 120.0
     X = (root[:, :, None, :] + skel[None]).reshape(-1, 3).contiguous()
     del root
     xy = cg.project(X)                                         # our own projection kernel
     C, N = xy.shape[0], xy.shape[1]
+    W, H = synth_image_size()
     for c in range(C):                                         # plane by plane: bounded temporaries
+        # a camera does not detect what falls outside its frame (also keeps the polynomial
+        # distortion model inside its monotone range)
+        off = (xy[c, :, 0] < 0) | (xy[c, :, 0] > W) | (xy[c, :, 1] < 0) | (xy[c, :, 1] > H)
+        xy[c][off] = float("nan")
         xy[c] += torch.randn((N, 2), generator=g, device=device, dtype=f64) * 0.3
         if workload == "ransac":
             o = torch.rand((N,), generator=g, device=device) < 0.2
@@ -345,14 +351,16 @@ def run_gpu(args):
     tf = ctypes_double()
     if rank == 0 and lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
         roofline["fp64_peak_tflops_measured"] = tf.value
-    extra = {}
+    extra = {"mean_valid_views": float((~torch.isnan(xy[:, :, 0])).double().mean().item() * C)}
     if args.workload == "ransac":
         extra["mean_subsets_per_point"] = float(nev.double().mean().item())
         extra["selected_fraction"] = float((~torch.isnan(p3d[:, 0])).double().mean().item())
 
     # ---- e2e: host buffers through the C-ABI host pipeline (H2D + kernel + D2H per step), every
     # rank streams its own shard concurrently ----
-    n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else N
+    # N = 1: the whole workload; N > 1: a 2e7-instance slice per rank (bounds the pinned host
+    # memory of 8 concurrent ranks), reported in joint_instances_per_gpu
+    n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else (N if world == 1 else min(N, 20000000))
     e2e = None
     try:
         if args.no_e2e:
@@ -427,6 +435,11 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def synth_image_size():
+    from macaque_3d_pose_estimation_b200 import synth
+    return synth.IMG_SIZE
 
 
 def ctypes_double():

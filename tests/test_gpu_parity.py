@@ -289,3 +289,60 @@ def test_gpu_distort_points_and_camera_models():
         X = synth.make_tracks(5, 2, seed=3).reshape(-1, 3)
         p2 = spec.project(X) + 1.0
         assert np.abs(cam.reprojection_error(X, p2) - 1.0).max() <= 1e-9
+
+
+@pytest.mark.slow
+def test_gpu_baseline_full_size_properties():
+    """BASELINE.json config 2 at FULL size (8 views, 4 x 17 x 1e6 = 6.8e7 joint-instances, device
+    resident) and config 3 shape at 1.36e7, checked through size-independent properties: a
+    random sample against the oracle, agreement of disjoint launches (slice == whole), and the
+    RANSAC selection re-scored by an independent kernel."""
+    import torch
+    from bench import make_device_workload
+    seed = 20261018 + 2
+    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    _, xy = make_device_workload(cg, 1000000, 4, 17, seed, "dlt", dev)
+    n = xy.shape[1]
+    assert n == 68000000
+    p3d, err = cg.triangulate_with_error(xy)
+    rng = np.random.default_rng(3)
+    idx = np.sort(rng.choice(n, 5000, replace=False))
+    tidx = torch.from_numpy(idx).to(dev)
+    sample = xy[:, tidx].cpu().numpy()
+    ref = og.triangulate(cams, sample)
+    got = p3d[tidx].cpu().numpy()
+    assert _eq_nan(got, ref) and np.nanmax(np.abs(got - ref)) <= P3D_TOL_MM
+    referr = og.reprojection_error(cams, ref, sample, mean=True)
+    # (two-view points with near-parallel rays: LAPACK's own noise reaches ~1e-6 mm / px)
+    assert np.nanmax(np.abs(err[tidx].cpu().numpy() - referr) / (1.0 + np.abs(referr))) <= 1e-5
+    # a slice launched on its own gives the same bits as the whole
+    lo, hi = 31234567, 31234567 + 100003
+    p3s, errs = cg.triangulate_with_error(xy[:, lo:hi].contiguous())
+    assert torch.equal(p3s.nan_to_num(), p3d[lo:hi].nan_to_num())
+    assert torch.equal(errs.nan_to_num(), err[lo:hi].nan_to_num())
+    # NaN pattern of the output == fewer than two valid views in the input
+    nvalid = (~torch.isnan(xy[:, :, 0])).sum(dim=0)
+    assert torch.equal(torch.isnan(p3d[:, 0]), nvalid < 2)
+    del xy, p3d, err, nvalid
+    torch.cuda.empty_cache()
+
+    _, xy = make_device_workload(cg, 200000, 4, 17, seed, "ransac", dev)
+    n = xy.shape[1]
+    out, picked, xyp, rerr, sidx, nev = cg.triangulate_ransac(xy, return_stats=True)
+    idx = np.sort(rng.choice(n, 3000, replace=False))
+    tidx = torch.from_numpy(idx).to(dev)
+    o = og.triangulate_ransac(cams, xy[:, tidx].cpu().numpy(), return_stats=True)
+    assert np.array_equal(picked[:, tidx].cpu().numpy(), o[1])
+    assert np.array_equal(sidx[tidx].cpu().numpy(), o[4]) and np.array_equal(nev[tidx].cpu().numpy(), o[5])
+    assert np.nanmax(np.abs(out[tidx].cpu().numpy() - o[0])) <= P3D_TOL_MM
+    assert (np.abs(rerr[tidx].cpu().numpy() - o[3]) / (1.0 + np.abs(o[3]))).max() <= 1e-5
+    # the reported error is the mean reprojection error of the selected views at the selected point
+    chk = cg.reprojection_error(out, xyp, mean=True)
+    sel = sidx >= 0
+    assert float(((chk[sel] - rerr[sel]).abs() / (1.0 + rerr[sel])).max()) <= 1e-9
+    assert torch.equal(torch.isnan(xyp[:, :, 0]), ~picked[:, :, 0])
+    # selected => error below the acceptance bound; early exit => below the 0.5 px threshold or arg-min
+    assert float(rerr[sel].max()) < 200.0
