@@ -144,13 +144,20 @@ M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, d
   const double x0 = (u - c.cx) * c.ifx;
   const double y0 = (v - c.cy) * c.ify;
   double x = x0, y = y0;
-  bool bail = false;  // OpenCV: "if (icdist < 0) { x = x0; y = y0; break; }"
+  // OpenCV: "if (icdist < 0) { x = x0; y = y0; break; }".  The sign bits of the five icdist
+  // values are OR-ed on the integer pipe; a set bit (icdist < 0, or -0 / negative NaN, which
+  // the literal transcription handles identically to this loop) replays the point through it.
+  int neg = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     const double r2 = x * x + y * y;
     double icdist = rcp(1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
     if (FULL) icdist *= 1.0 + ((c.k[7] * r2 + c.k[6]) * r2 + c.k[5]) * r2;
-    bail = bail || (icdist < 0.0);
+#if defined(__CUDA_ARCH__)
+    neg |= __double2hiint(icdist);
+#else
+    neg |= (icdist < 0.0) ? -1 : 0;
+#endif
     const double x2 = x + x, y2 = y + y;
     const double xy2 = x2 * y;
     double dx = c.k[2] * xy2 + c.k[3] * (x2 * x + r2);
@@ -162,7 +169,7 @@ M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, d
     x = (x0 - dx) * icdist;
     y = (y0 - dy) * icdist;
   }
-  if (bail) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
+  if (neg < 0) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
   xo = x;
   yo = y;
 }
