@@ -411,6 +411,43 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
+    # ---- secondary line: BASELINE config 3 (subset RANSAC, 20 % outliers) on a 1e5-frame slice ----
+    if args.workload == "dlt" and not args.no_ransac_extra:
+        try:
+            del xy
+            torch.cuda.empty_cache()
+            Fr = 100000
+            _, xyr = make_device_workload(cg, Fr, A, J, seed + 100, "ransac", device)
+            Nr = xyr.shape[1]
+            r3 = torch.empty((Nr, 3), dtype=torch.float64, device=device)
+            re_ = torch.empty((Nr,), dtype=torch.float64, device=device)
+            rp = torch.empty((C, Nr), dtype=torch.uint8, device=device)
+            rx = torch.empty((C, Nr, 2), dtype=torch.float64, device=device)
+            rn = torch.empty((Nr,), dtype=torch.int32, device=device)
+
+            def rstep():
+                _lib.check(lib.m3d_triangulate_ransac(rig.handle, xyr.data_ptr(), Nr, 1, 2, 0.5, 200.0, r3.data_ptr(),
+                                                      rp.data_ptr(), rx.data_ptr(), re_.data_ptr(), None, rn.data_ptr(),
+                                                      stream.cuda_stream), "ransac step")
+            for _ in range(3):
+                rstep()
+            torch.cuda.synchronize()
+            r0 = torch.cuda.Event(enable_timing=True)
+            r1 = torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(5):
+                rstep()
+            r1.record(stream)
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1) / 5
+            extra["ransac"] = {
+                "workload": "cfg3: 8-view triangulate_ransac (all camera subsets, min_cams=2), 20% outlier detections",
+                "value": Nr / (rms * 1e-3), "unit": "joint-instances/s (one GPU)", "joint_instances": Nr,
+                "ms_per_step": rms, "mean_subsets_per_point": float(rn.double().mean().item()),
+                "roofline_frac_hbm": 296 * Nr / (rms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_instance": 296}
+        except Exception as ex:  # pragma: no cover
+            extra["ransac"] = {"error": str(ex)[:200]}
+
     # ---- CPU baseline: loop-faithful port, one core, bounded sample ---------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -463,6 +500,7 @@ def main():
     ap.add_argument("--e2e-points", type=int, default=0, help="joint-instances of the e2e run (0 = all)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ransac-extra", action="store_true")
     args = ap.parse_args()
     if args.frames <= 0:
         args.frames = 1000000 if args.workload == "dlt" else 200000
