@@ -179,3 +179,151 @@ def calc_3dpose(kp_2d, config_path=None, camparam=None, thr_kp=THR_KP):
     und = cg.undistort_points(np.ascontiguousarray(kp[:, :, :2]))
     use = ~(np.isnan(kp[:, :, 0]) | (kp[:, :, 2] < thr_kp))
     return triangulate_ls_batch(cg, und, use)
+
+
+# ------------------------------------------------------------------------------------------
+# keyframe association (MultiEstimator.predict_data, step2_crossviewmatching.py:502-713)
+# ------------------------------------------------------------------------------------------
+
+ALPHA_ID = 0.2          # step2:22
+MODEL_CFG = {"joint_num": 17, "alpha_SVT": 0.5, "lambda_SVT": 50, "dual_stochastic_SVT": False}   # step2:25-31
+
+
+def reproject(i_cam, p3d, camparam=None, config_path=""):
+    """step2_crossviewmatching.py:465-489: project (n,3) points into camera i_cam (omnidir model)."""
+    cg = group_from_camparam(camparam)
+    return cg.cameras[i_cam].project(np.asarray(p3d, dtype=np.float64)).reshape(-1, 2)
+
+
+class MultiEstimator:
+    """Matching and 3D reconstruction across cameras for a single keyframe — the host logic of
+    step2_crossviewmatching.py:494-713 with every geometric step on the GPU kernels
+    (ray affinity, SVT association, LS triangulation, omnidir reprojection).  Drawing
+    (``show=True``) and the unused spectral initialisation (:577-586) are not reproduced."""
+
+    def __init__(self, cfg=None, debug=False):
+        self.cfg = cfg
+        self.debug = debug
+
+    def predict_data(self, info_dict, show=False, plt_id=0, camparam=None, bcomb_prev=None):
+        import itertools
+        _need_camparam(camparam)
+        if show:
+            raise NotImplementedError("predict_data(show=True) draws with matplotlib (step2:648-693)")
+        n_cam = len(info_dict)
+        dimGroup = [0]
+        cnt = 0
+        for cam_id in range(n_cam):
+            cnt += len(info_dict[cam_id][0])
+            dimGroup.append(cnt)
+        dimGroup = np.array(dimGroup)
+        info_list = []
+        for cam_id in range(n_cam):
+            info_list.extend(info_dict[cam_id][0])
+        if not info_list:
+            return [], [], []
+        M = len(info_list)
+        n_kp = MODEL_CFG["joint_num"]
+        pose2d = np.array([det["pose2d"] for det in info_list]).reshape(M, n_kp, 2)
+        pose_score = np.array([det["pose2d_raw"] for det in info_list]).reshape(M, n_kp, 3)[..., 2]
+        kp_mat = np.concatenate([pose2d, pose_score[..., np.newaxis]], axis=2)
+        sub2cam = np.zeros(M, dtype=int)
+        for idx in range(len(dimGroup) - 1):
+            sub2cam[dimGroup[idx]:dimGroup[idx + 1]] = idx
+        cid_list = [det["cid"] for det in info_list]
+
+        geo_aff = geometry_affinity2(kp_mat.copy(), dimGroup, self.cfg, camparam=camparam)      # :554
+        cid = np.asarray(cid_list)
+        cid_mat = ((sub2cam[:, None] != sub2cam[None, :]) & (cid[:, None] >= 0) &
+                   (cid[:, None] == cid[None, :])).astype(np.float64)                          # :557-561
+        W = ALPHA_ID * cid_mat + (1 - ALPHA_ID) * geo_aff                                      # :572-575
+        W *= (geo_aff > 0)
+        W = np.nan_to_num(W)
+        match_mat = matchSVT(W, dimGroup, alpha=MODEL_CFG["alpha_SVT"], _lambda=MODEL_CFG["lambda_SVT"],
+                             dual_stochastic_SVT=MODEL_CFG["dual_stochastic_SVT"])              # :589-595
+        col_sums = match_mat.sum(axis=0)                                                       # :598-607
+        matched_cols = np.nonzero(col_sums > 1.9)[0]
+        bin_match = match_mat[:, matched_cols] > 0.9
+        matched_list = [[] for _ in range(bin_match.shape[1])]
+        for sub_idx, row in enumerate(bin_match):
+            if row.sum() != 0:
+                matched_list[row.argmax()].append(sub_idx)
+        matched_list = [np.array(lst) for lst in matched_list]
+
+        def get_best_comb(person_idxs):                                                        # :610-646
+            person_idxs = np.asarray(person_idxs, dtype=int)
+            cam_ids = sub2cam[person_idxs]
+            cam_groups = [person_idxs[np.where(cam_ids == c)].tolist() or [None] for c in range(n_cam)]
+            combos = list(itertools.product(*cam_groups))
+            if len(combos) == 1:
+                return person_idxs
+            errors = []
+            for combo in combos:
+                kp2d = np.zeros((n_cam, n_kp, 3))
+                for c, sub_idx in enumerate(combo):
+                    if sub_idx is not None:
+                        kp2d[c] = info_list[sub_idx]["pose2d_raw"]
+                p3d = calc_3dpose(kp2d, self.cfg, camparam=camparam)
+                derrs = []
+                for c, sub_idx in enumerate(combo):
+                    if sub_idx is None:
+                        continue
+                    raw = np.asarray(info_list[sub_idx]["pose2d_raw"])
+                    ok = raw[:, 2] > THR_KP
+                    derrs.append(raw[ok, :2] - reproject(c, p3d, camparam=camparam)[ok])
+                errors.append(np.sqrt((np.vstack(derrs) ** 2).mean()) if derrs else np.inf)
+            best = combos[int(np.argmin(errors))]
+            return np.array([i for i in best if i is not None], dtype=int)
+
+        refined = []
+        for person in matched_list:                                                            # :649-657
+            best = get_best_comb(person)
+            refined.append(best)
+            leftover = set(person.tolist()) - set(best.tolist())
+            if len(leftover) > 1:
+                refined.append(get_best_comb(np.array(list(leftover), dtype=int)))
+        P3d_list, matched_list2, bcomb_list = [], [], []
+        for person_idxs in refined:                                                            # :696-713
+            if person_idxs.shape[0] < 2:
+                continue
+            kp2d = np.zeros((n_cam, n_kp, 3))
+            for sub_idx in person_idxs:
+                kp2d[sub2cam[sub_idx]] = info_list[sub_idx]["pose2d_raw"]
+            P3d_list.append(calc_3dpose(kp2d, self.cfg, camparam=camparam))
+            bcomb = -np.ones(n_cam, dtype=int)
+            for sub_idx in person_idxs:
+                bcomb[sub2cam[sub_idx]] = info_list[sub_idx]["bbox_id"][1]
+            matched_list2.append(person_idxs)
+            bcomb_list.append(bcomb)
+        return matched_list2, P3d_list, bcomb_list
+
+
+# ------------------------------------------------------------------------------------------
+# step 3 users of the same arithmetic (step3_crossframematching.py:254-302)
+# ------------------------------------------------------------------------------------------
+
+def calc_3dpose_batch(kp_2d, camparam, thr_kp=0.3):
+    """All frames of a tracklet in one launch: kp_2d (F,C,J,3) raw pixels + score (NaN rows for
+    cameras that do not see the animal) -> (F,J,3).  Per frame this is step3's calc_3dpose
+    (:254-272, score gate 0.3) = omnidir undistortion + mct.triangulatePoints."""
+    cg = group_from_camparam(camparam)
+    kp = np.asarray(kp_2d, dtype=np.float64)
+    F, C, J, _ = kp.shape
+    flat = np.ascontiguousarray(kp.transpose(1, 0, 2, 3)).reshape(C, F * J, 3)
+    und = cg.undistort_points(np.ascontiguousarray(flat[:, :, :2]))
+    with np.errstate(invalid="ignore"):
+        use = ~(np.isnan(flat[:, :, 0]) | (flat[:, :, 2] < thr_kp))
+    return triangulate_ls_batch(cg, np.nan_to_num(und), use).reshape(F, J, 3)
+
+
+def calc_3dtrace(p2d, camparam, thr_kp=0.3):
+    """step3's calc_3dtrace (:274-302) on the (F,C,J,3) array it assembles per tracklet: frames
+    seen by fewer than two cameras give NaN; returns the per-frame nanmedian over keypoints (F,3)."""
+    import warnings
+    kp = np.asarray(p2d, dtype=np.float64)
+    p3d = calc_3dpose_batch(kp, camparam, thr_kp)
+    seen = (~np.isnan(kp[:, :, :, 0]).all(axis=2)).sum(axis=1)
+    p3d[seen < 2] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        return np.nanmedian(p3d, axis=1)

@@ -73,3 +73,80 @@ def test_gpu_crossview_golden(name):
         assert not mb[f, m:].any() and not mb[f, :, m:].any()
         _, it_ref, _ = ocv.match_svt(g["f%d_W" % f], g["f%d_dimGroup" % f], alpha=0.5, lam=50.0, return_info=True)
         assert abs(int(its[f]) - it_ref) <= 2
+
+
+def test_gpu_keyframe_association_recovers_animals():
+    """MultiEstimator.predict_data (step2:502-713) on a synthetic omnidir rig, 6 animals x 8 views:
+    the clusters must be the animals and the 3D poses the ground truth.  (The reference's own
+    predict_data needs cv2.omnidir and cannot run here — a functional check, not a parity one.)"""
+    from macaque_3d_pose_estimation_b200 import synth
+    from oracle import cameragroup as og
+    C, A, J = 8, 6, 17
+    dicts = synth.make_rig(C, "omnidir", seed=41)
+    cams = fixtures.cams_from_dicts(dicts)
+    cp = {"camera_id": [d["name"] for d in dicts], "K": [np.array(d["K"]) for d in dicts],
+          "xi": [np.array(d["xi"]).reshape(1, 1) for d in dicts], "D": [np.array(d["D"]).reshape(1, 4) for d in dicts],
+          "rvecs": [np.array(d["rotation"]).reshape(3, 1) for d in dicts],
+          "tvecs": [np.array(d["translation"]).reshape(3, 1) for d in dicts], "pmat": None}
+    rng = np.random.default_rng(41)
+    X = synth.make_tracks(1, A, seed=41)[0] * np.array([0.6, 0.6, 0.5])          # keep every view in frame
+    info = {}
+    for c in range(C):
+        dets = []
+        for a in rng.permutation(A):
+            raw = cams[c].project(X[a]) + rng.normal(0, 0.3, size=(J, 2))
+            sc = rng.uniform(0.4, 1.0, size=J)
+            und = cams[c].undistort(raw)
+            dets.append({"pose2d": und, "pose2d_raw": np.concatenate([raw, sc[:, None]], axis=1), "bbox": [0, 0, 1, 1],
+                         "bbox_id": (c, int(a)), "cid": -1})
+        info[c] = [dets]
+    est = cv.MultiEstimator(cfg=None)
+    matched, P3d, bcomb = est.predict_data(info, camparam=cp)
+    assert len(matched) == A
+    seen = set()
+    for idxs, p3, bc in zip(matched, P3d, bcomb):
+        assert len(idxs) == C and (bc >= 0).all()
+        assert len(set(bc.tolist())) == 1                        # one animal per cluster
+        a = int(bc[0])
+        seen.add(a)
+        assert np.abs(p3 - X[a]).max() < 2.0                      # mm, 0.3 px detector noise
+    assert seen == set(range(A))
+
+
+def test_gpu_step3_batch_triangulation():
+    """calc_3dpose_batch / calc_3dtrace (step3_crossframematching.py:254-302) against the oracle's
+    per-frame mct.triangulatePoints restatement, omnidir rig, score gate 0.3."""
+    from macaque_3d_pose_estimation_b200 import synth
+    from oracle import cameragroup as og
+    C, J, F = 8, 17, 60
+    dicts = synth.make_rig(C, "omnidir", seed=43)
+    cams = fixtures.cams_from_dicts(dicts)
+    cp = {"camera_id": [d["name"] for d in dicts], "K": [np.array(d["K"]) for d in dicts],
+          "xi": [np.array(d["xi"]).reshape(1, 1) for d in dicts], "D": [np.array(d["D"]).reshape(1, 4) for d in dicts],
+          "rvecs": [np.array(d["rotation"]).reshape(3, 1) for d in dicts],
+          "tvecs": [np.array(d["translation"]).reshape(3, 1) for d in dicts], "pmat": None}
+    rng = np.random.default_rng(43)
+    X = synth.make_tracks(F, 1, seed=43)[:, 0] * np.array([0.6, 0.6, 0.5])
+    kp = np.empty((F, C, J, 3))
+    for c in range(C):
+        kp[:, c, :, :2] = cams[c].project(X.reshape(-1, 3)).reshape(F, J, 2) + rng.normal(0, 0.3, size=(F, J, 2))
+    kp[..., 2] = rng.uniform(0.1, 1.0, size=(F, C, J))
+    kp[rng.random((F, C)) < 0.3] = np.nan                         # camera does not see the animal
+    got = cv.calc_3dpose_batch(kp, cp, thr_kp=0.3)
+    for f in range(0, F, 7):
+        und = np.stack([cams[c].undistort(kp[f, c, :, :2]) for c in range(C)])
+        with np.errstate(invalid="ignore"):
+            use = ~(np.isnan(kp[f, :, :, 0]) | (kp[f, :, :, 2] < 0.3))
+        ref = ocv.triangulate_ls(cams, np.nan_to_num(und), use.T)
+        assert np.array_equal(np.isnan(got[f]), np.isnan(ref))
+        assert np.nanmax(np.abs(got[f] - ref), initial=0.0) <= 1e-6
+    trace = cv.calc_3dtrace(kp, cp)
+    assert trace.shape == (F, 3)
+    seen = (~np.isnan(kp[:, :, :, 0]).all(axis=2)).sum(axis=1)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        ref_trace = np.nanmedian(np.where((seen < 2)[:, None, None], np.nan, got), axis=1)
+    assert np.array_equal(trace, ref_trace, equal_nan=True)
+    ok = ~np.isnan(trace[:, 0])
+    assert ok.sum() > F // 2 and np.abs(trace[ok] - np.median(X[ok], axis=1)).max() < 100.0
