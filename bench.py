@@ -211,7 +211,7 @@ def run_reference(args):
         "unit": "joint-instances/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
         "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, 8, n),
+        "config": config_dict(args, 8, args.frames * 4 * 17),     # the workload of our arm; see cpu_baseline.sample
         "cpu_baseline": {"value": value, "unit": "joint-instances/s", "cores": procs, "kind": "port",
                          "sample": "%d joint-instances per step (cfg-1 rig: 8 pinhole cameras, 2 animals x 17 "
                                    "joints), loop-faithful NumPy/OpenCV port of the reference in oracle/, "
