@@ -154,12 +154,12 @@ def _cpu_chunk(args):
     return p2d.shape[1]
 
 
-def cpu_workload(workload, n_points, seed):
+def cpu_workload(workload, n_points, seed, n_cams=8):
     import numpy as np
     from macaque_3d_pose_estimation_b200 import synth
     from oracle import cameragroup as og
     from oracle import fixtures
-    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    dicts = synth.make_rig(n_cams, "pinhole", seed=seed)
     cams = fixtures.cams_from_dicts(dicts)
     n_frames = max(1, n_points // (2 * 17))
     X = synth.make_tracks(n_frames, 2, seed=seed).reshape(-1, 3)[:n_points]
@@ -168,10 +168,10 @@ def cpu_workload(workload, n_points, seed):
     return dicts, p2d
 
 
-def time_cpu(workload, n_points, procs, seed=20261018):
+def time_cpu(workload, n_points, procs, seed=20261018, n_cams=8):
     """joint-instances/s of the loop-faithful port on `procs` host processes."""
     import numpy as np
-    dicts, p2d = cpu_workload(workload, n_points, seed)
+    dicts, p2d = cpu_workload(workload, n_points, seed, n_cams)
     n = p2d.shape[1]
     if procs <= 1:
         _cpu_chunk((dicts, p2d[:, :8], workload))              # warm caches / imports
@@ -201,7 +201,7 @@ def run_reference(args):
     vals = []
     t_all = time.perf_counter()
     for i in range(args.steps):
-        v, n = time_cpu(args.workload, sample, procs)
+        v, n = time_cpu(args.workload, sample, procs, n_cams=args.cameras)
         vals.append(v)
         if time.perf_counter() - t_all > 240:
             break
@@ -211,9 +211,9 @@ def run_reference(args):
         "unit": "joint-instances/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
         "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, 8, args.frames * 4 * 17),     # the workload of our arm; see cpu_baseline.sample
+        "config": config_dict(args, args.cameras, args.frames * 4 * 17),     # the workload of our arm; see cpu_baseline.sample
         "cpu_baseline": {"value": value, "unit": "joint-instances/s", "cores": procs, "kind": "port",
-                         "sample": "%d joint-instances per step (cfg-1 rig: 8 pinhole cameras, 2 animals x 17 "
+                         "sample": "%d joint-instances per step (cfg-1 rig: pinhole cameras, 2 animals x 17 "
                                    "joints), loop-faithful NumPy/OpenCV port of the reference in oracle/, "
                                    "%d spawn processes" % (n, procs)},
         "e2e": {"value": value, "unit": "joint-instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,9 +223,9 @@ def run_reference(args):
 
 
 def config_dict(args, C, n_per_gpu):
-    names = {"dlt": "cfg2: 8-view undistort + DLT triangulate + mean reprojection_error, 4 macaques x 17 joints",
-             "ransac": "cfg3: 8-view triangulate_ransac (all camera subsets, min_cams=2), 20% outlier detections"}
-    return {"workload": names[args.workload], "cameras": C, "camera_model": "pinhole(5 coeff)",
+    names = {"dlt": "cfg2: %d-view undistort + DLT triangulate + mean reprojection_error, 4 macaques x 17 joints",
+             "ransac": "cfg3: %d-view triangulate_ransac (all camera subsets, min_cams=2), 20%% outlier detections"}
+    return {"workload": names[args.workload] % C, "cameras": C, "camera_model": "pinhole(5 coeff)",
             "joint_instances_per_gpu": int(n_per_gpu), "frames_per_gpu": int(args.frames),
             "animals": 4, "joints": 17, "missing_views": 0.1,
             "outliers": 0.2 if args.workload == "ransac" else 0.0,
@@ -254,7 +254,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.require_gpu()
 
-    C, A, J = 8, 4, 17
+    C, A, J = args.cameras, 4, 17
     F = args.frames
     seed = 20261018 + 2 + rank
     cg = CameraGroup.from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2))
@@ -452,7 +452,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         n_cpu = 34000 if args.workload == "dlt" else 340
-        v, n = time_cpu(args.workload, n_cpu, 1)
+        v, n = time_cpu(args.workload, n_cpu, 1, n_cams=C)
         cpu = {"value": v, "unit": "joint-instances/s", "cores": 1, "kind": "port",
                "sample": "%d joint-instances of the cfg-1 rig (8 pinhole cameras), loop-faithful NumPy/OpenCV "
                          "port of the reference (oracle/cameragroup.py *_loops)" % n}
@@ -498,6 +498,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6 dlt, 2e5 ransac)")
     ap.add_argument("--e2e-points", type=int, default=0, help="joint-instances of the e2e run (0 = all)")
+    ap.add_argument("--cameras", type=int, default=8, help="cameras of the synthetic ring rig (BASELINE: 8; config 5: 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ransac-extra", action="store_true")
