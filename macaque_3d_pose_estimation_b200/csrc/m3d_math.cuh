@@ -388,12 +388,37 @@ M3D_HD void gram_add_row(Gram& G, double a0, double a1, double a2, double a3) {
   G.w += a3 * a3;
 }
 
+// G += (s a)(a)^T for a signed row (sa = sign * a)
+M3D_HD void gram_add_row(Gram& G, double s0, double s1, double s2, double s3, double a0, double a1,
+                         double a2, double a3) {
+  G.h[0] += s0 * a0;
+  G.h[1] += s0 * a1;
+  G.h[2] += s0 * a2;
+  G.h[3] += s1 * a1;
+  G.h[4] += s1 * a2;
+  G.h[5] += s2 * a2;
+  G.g[0] += s0 * a3;
+  G.g[1] += s1 * a3;
+  G.g[2] += s2 * a3;
+  G.w += s3 * a3;
+}
+
 // rows of camera c for the undistorted observation (x, y)   (cameras.py:27-28)
 M3D_HD void gram_add_camera(Gram& G, const CamDev& c, double x, double y) {
   gram_add_row(G, x * c.R[6] - c.R[0], x * c.R[7] - c.R[1], x * c.R[8] - c.R[2],
                x * c.t[2] - c.t[0]);
   gram_add_row(G, y * c.R[6] - c.R[3], y * c.R[7] - c.R[4], y * c.R[8] - c.R[5],
                y * c.t[2] - c.t[1]);
+}
+
+// signed accumulation (sign = +1 / -1): toggling a camera in or out of a running Gram sum
+M3D_HD void gram_acc_camera(Gram& G, const CamDev& c, double x, double y, double sign) {
+  const double a0 = x * c.R[6] - c.R[0], a1 = x * c.R[7] - c.R[1], a2 = x * c.R[8] - c.R[2],
+               a3 = x * c.t[2] - c.t[0];
+  const double b0 = y * c.R[6] - c.R[3], b1 = y * c.R[7] - c.R[4], b2 = y * c.R[8] - c.R[5],
+               b3 = y * c.t[2] - c.t[1];
+  gram_add_row(G, sign * a0, sign * a1, sign * a2, sign * a3, a0, a1, a2, a3);
+  gram_add_row(G, sign * b0, sign * b1, sign * b2, sign * b3, b0, b1, b2, b3);
 }
 
 M3D_HD void gram_add(Gram& G, const Gram& B) {
@@ -465,20 +490,27 @@ M3D_HD_NOINLINE void dlt_solve_jacobi(const Gram& G, double& X, double& Y, doubl
 // (measured: <= 2e-11 px in mean reprojection error vs extended precision; LAPACK's SVD
 // of the DLT matrix: ~1e-10 px).
 M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
-  double lam = 0.0;
+  double lam = 0.0, lam_pd = 0.0;  // lam_pd: last shift at which H - lam I was positive definite
   double x0 = 0.0, x1 = 0.0, x2 = 0.0;
   bool ok = false;
   const double tr = G.h[0] + G.h[3] + G.h[5];
   const double itr2 = rcp(tr * tr);
 #pragma unroll 1
-  for (int it = 0; it < 12; ++it) {
+  for (int it = 0; it < 16; ++it) {
     const double a = G.h[0] - lam, b = G.h[1], c = G.h[2], d = G.h[3] - lam, e = G.h[4],
                  f = G.h[5] - lam;
     const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
     const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
     const double det = a * c00 + b * c01 + c * c02;
-    // positive definite (Sylvester) <=> lam < lam_min(H): we are on the right branch
-    if (!(a > 0.0 && c22 > 0.0 && det > 0.0)) break;
+    // positive definite (Sylvester) <=> lam < lam_min(H): we are on the right branch.  The
+    // first Newton step (from the left of the root of a concave f) overshoots; with gross
+    // outliers in the subset it can jump past the pole lam_min(H): halve it back.
+    if (!(a > 0.0 && c22 > 0.0 && det > 0.0)) {
+      if (it == 0 || !(lam > lam_pd)) break;  // H itself is not positive definite: degenerate
+      lam = 0.5 * (lam + lam_pd);
+      continue;
+    }
+    lam_pd = lam;
     // p = adj(H - lam I) g = -det X.  The Newton step f / (1 + |X|^2) needs one reciprocal
     // in this form (and no 1/det on the dependency chain):
     //   f = w - lam - (g.p)/det ,  1 + |X|^2 = (det^2 + |p|^2)/det^2
@@ -487,11 +519,16 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
     const double p2 = c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2];
     const double q = G.g[0] * p0 + G.g[1] * p1 + G.g[2] * p2;
     const double pp = p0 * p0 + p1 * p1 + p2 * p2;
-    const double dl = det * ((G.w - lam) * det - q) * rcp(det * det + pp);
+    const double num = (G.w - lam) * det - q;
+    const double iden = rcp(det * det + pp);
+    const double dl = det * num * iden;
     // lam_min(H - lam I) >= det / tr^2 ; a step below 1e-7 of that changes X by < 1e-14 |X|
-    // beyond the first-order correction applied here.
+    // beyond the first-order correction applied here.  A step at the rounding-noise level of
+    // its own numerator (near-parallel rays: lam_min(H) -> 0) cannot be improved in fp64
+    // either: finish there as well.
     const double mu_lb = det * itr2;
-    if (fabs(dl) <= 1e-7 * mu_lb) {
+    const double noise = 4e-16 * (fabs(G.w - lam) * det + fabs(q)) * det * iden;
+    if (fabs(dl) <= 1e-7 * mu_lb || fabs(dl) <= noise) {
       const double idet = rcp(det);
       x0 = -p0 * idet;
       x1 = -p1 * idet;
@@ -503,7 +540,7 @@ M3D_HD void dlt_solve(const Gram& G, double& X, double& Y, double& Z) {
       x0 += dl * y0;
       x1 += dl * y1;
       x2 += dl * y2;
-      ok = true;
+      ok = (x0 == x0);
       break;
     }
     lam += dl;

@@ -210,7 +210,11 @@ def test_gpu_large_n_properties():
     assert np.nanmax(np.abs(out[idx[:2000]] - o[0])) <= P3D_TOL_MM
     tr = cg.triangulate_ransac(t, return_stats=True)
     assert np.array_equal(tr[1].cpu().numpy(), picked[:, perm])
-    assert np.array_equal(tr[0].cpu().numpy(), out[perm], equal_nan=True)
+    assert np.array_equal(tr[4].cpu().numpy(), sidx[perm]) and np.array_equal(tr[5].cpu().numpy(), nev[perm])
+    # (which of the two search kernels finishes a point depends on its neighbours in the sorted
+    # order, and their Gram sums associate differently: last-bit differences in p3d are allowed)
+    assert _eq_nan(tr[0].cpu().numpy(), out[perm])
+    assert np.nanmax(np.abs(tr[0].cpu().numpy() - out[perm])) <= 1e-9
     # selected points: reprojection error of the selection is what was reported
     sel = sidx >= 0
     chk = cg.reprojection_error(out, np.where(picked, p2, np.nan), mean=True)
