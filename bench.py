@@ -58,7 +58,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -67,7 +67,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, t0, t1):
+        """wall-clock window of the timed region: only samples inside it are reported"""
+        self.window = (t0, t1)
 
     def stop(self):
         if self.proc is None:
@@ -79,7 +83,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        win = getattr(self, "window", None)
+        inside = [ln for (t, ln) in self.lines if win and win[0] - 0.02 <= t <= win[1] + 0.02]
+        use = inside if len(inside) >= 2 else [ln for (_, ln) in self.lines]
+        for ln in use:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -297,11 +304,13 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
+    t_wall0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.mark(t_wall0, time.time())
     ms = e0.elapsed_time(e1)
     launches = lib.m3d_launch_count() - launches0
     if world > 1:
