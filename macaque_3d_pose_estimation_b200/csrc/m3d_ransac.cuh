@@ -44,10 +44,17 @@ __host__ __device__ inline size_t ransac_rig_bytes() { return (sizeof(RigDev) + 
 // per-point record handed from k_ransac_full to k_ransac_search to k_ransac_emit
 struct RansacSlot {
   double best_err, bx, by, bz;
-  unsigned long long ord;  // cameras by decreasing residual at the full-set solution, 4 bits each
-  uint32_t vmask, umask, best_mask;
+  // suspicion order (cameras by decreasing residual at the full-set solution), 4 bits each.
+  //   C > 8 : nibble r = camera of rank r
+  //   C <= 8: low word  "ordl":  nibble r = LOCAL index of the valid camera of rank r,
+  //           high word "lrank": nibble b = rank of local camera b
+  // (local index b of a valid camera = the bit of the enumeration step s that drops it)
+  unsigned long long ord;
+  uint32_t masks;  // vmask | umask << 16
+  uint32_t vlist;  // C <= 8: nibble b = camera dropped by bit b of s  (= V[k-1-b])
   int32_t best_s, neval;
   int32_t decided;  // 1: nothing left to search
+  uint32_t uml;     // C <= 8: usable (post-undistortion) cameras as a mask over local indices
 };
 static_assert(sizeof(RansacSlot) == 64, "RansacSlot layout");
 
@@ -74,6 +81,37 @@ __device__ __forceinline__ int next_member(unsigned long long ord, int C, uint32
   return -1;
 }
 
+// Local camera numbering of one point for the <= 8-camera search kernel: local index b of a
+// valid camera is the bit of s that drops it (b = 0 is the LAST valid camera).  ord: nibble
+// r = physical camera of rank r (all C cameras, the invalid ones last or anywhere).
+__device__ __forceinline__ void local_lists(uint32_t vmask, uint32_t umask, unsigned long long ord, int C,
+                                            uint32_t& vlist, uint32_t& ordl, uint32_t& lrank, uint32_t& uml) {
+  vlist = 0;
+  ordl = 0;
+  lrank = 0;
+  uml = 0;
+  int b = 0;
+#pragma unroll
+  for (int c = 7; c >= 0; --c) {
+    if (c < C && ((vmask >> c) & 1u)) {
+      vlist |= (uint32_t)c << (4 * b);
+      uml |= ((umask >> c) & 1u) << b;
+      ++b;
+    }
+  }
+  int rr = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int c = (int)((ord >> (4 * r)) & 15ull);
+    if (r < C && ((vmask >> c) & 1u)) {
+      const int lb = __popc(vmask >> (c + 1));
+      ordl |= (uint32_t)lb << (4 * rr);
+      lrank |= (uint32_t)rr << (4 * lb);
+      ++rr;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // full-set pass: thread = point
 // ---------------------------------------------------------------------------------------
@@ -82,7 +120,8 @@ __global__ void __launch_bounds__(256, 2)
 k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t ld, int64_t n0,
               int64_t n, int undistort, int min_cams, double thr, double init_best,
               double* __restrict__ U, RansacSlot* __restrict__ slots) {
-  // xy: (C, ld, 2) planes, this launch covers points [n0, n0 + n); U: (C, n, 2); slots: (n)
+  // xy: (C, ld, 2) planes, this launch covers points [n0, n0 + n); U: (C, n, 2) receives the
+  // undistorted views; slots: (n)
   const int C = NC > 0 ? NC : rig.n_cams;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -90,19 +129,20 @@ k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
     unsigned long long ord = 0;
     double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
     int32_t best_s = -1;
-    uint32_t best_mask = 0;
     bool done = false;
     Gram G;
     gram_zero(G);
     if (NC > 0) {
       double2 raw[NC > 0 ? NC : 1];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) raw[c] = ld_xy(xy, (int64_t)c * ld + n0 + i);
+      for (int c = 0; c < NC; ++c) {
+        raw[c] = ld_xy(xy, (int64_t)c * ld + n0 + i);
+        if (raw[c].x == raw[c].x) vmask |= 1u << c;  // validity on the RAW x (cameras.py:658-659)
+      }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         double x = raw[c].x, y = raw[c].y;
-        if (raw[c].x == raw[c].x) {  // validity on the RAW x (cameras.py:658-659)
-          vmask |= 1u << c;
+        if ((vmask >> c) & 1u) {
           if (undistort) undistort_point<FULL, PO>(rig.cam[c], raw[c].x, raw[c].y, x, y);
           if (x == x) {  // survives inside triangulate (cameras.py:630)
             umask |= 1u << c;
@@ -138,7 +178,6 @@ k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
         if (e0 < best_err) {
           best_err = e0;
           best_s = 0;
-          best_mask = vmask;
           bx = X;
           by = Y;
           bz = Z;
@@ -200,7 +239,6 @@ k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
         if (e0 < best_err) {
           best_err = e0;
           best_s = 0;
-          best_mask = vmask;
           bx = X;
           by = Y;
           bz = Z;
@@ -215,10 +253,18 @@ k_ransac_full(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
     sl.bx = bx;
     sl.by = by;
     sl.bz = bz;
-    sl.ord = ord;
-    sl.vmask = vmask;
-    sl.umask = umask;
-    sl.best_mask = best_mask;
+    if (C <= 8) {
+      uint32_t vlist, ordl, lrank, uml;
+      local_lists(vmask, umask, ord, NC > 0 ? NC : C, vlist, ordl, lrank, uml);
+      sl.ord = (unsigned long long)ordl | ((unsigned long long)lrank << 32);
+      sl.vlist = vlist;
+      sl.uml = uml;
+    } else {
+      sl.ord = ord;
+      sl.vlist = 0;
+      sl.uml = 0;
+    }
+    sl.masks = vmask | (umask << 16);
     sl.best_s = best_s;
     sl.neval = 1;  // the full set is always tried (cameras.py:691)
     sl.decided = done ? 1 : 0;
@@ -303,8 +349,8 @@ k_ransac_search(const RigDev* __restrict__ rig_g, const double* __restrict__ xy,
     if (__any_sync(FULLM, fresh)) {
       if (fresh) {
         const RansacSlot* sl = slots + cur;
-        vm = sl->vmask;
-        um = sl->umask;
+        vm = sl->masks & 0xffffu;
+        um = sl->masks >> 16;
         ordp = sl->ord;
         k = __popc(vm);
         n_sub = 1u << k;
@@ -422,7 +468,6 @@ k_ransac_search(const RigDev* __restrict__ rig_g, const double* __restrict__ xy,
           RansacSlot* sl = slots + cur;
           sl->best_err = el;
           sl->best_s = (int32_t)(base + l);
-          sl->best_mask = cml;
           sl->bx = Xl;
           sl->by = Yl;
           sl->bz = Zl;
@@ -470,6 +515,8 @@ k_ransac_emit(int C, const double* __restrict__ xy, int64_t ld, int64_t n0, int6
        i += (int64_t)gridDim.x * blockDim.x) {
     const RansacSlot sl = slots[i];
     const int64_t o = n0 + i;
+    const uint32_t vmask = sl.masks & 0xffffu;
+    const uint32_t best_mask = sl.best_s >= 0 ? subset_mask(vmask, __popc(vmask), (uint32_t)sl.best_s) : 0u;
     p3d[3 * o] = sl.bx;
     p3d[3 * o + 1] = sl.by;
     p3d[3 * o + 2] = sl.bz;
@@ -479,7 +526,7 @@ k_ransac_emit(int C, const double* __restrict__ xy, int64_t ld, int64_t n0, int6
     if (picked || xy_picked) {
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
-        const bool in = (sl.best_mask >> c) & 1u;
+        const bool in = (best_mask >> c) & 1u;
         if (picked) picked[(int64_t)c * ld + o] = in ? 1 : 0;
         if (xy_picked) {
           double2 q = make_double2(qnan(), qnan());

@@ -54,3 +54,33 @@ def reconstruct(cgroup, kp2d_f, score_threshold=0.5, ransac=False, optim=False, 
     E[few] = np.nan
     num_cams[few] = np.nan
     return {'kp3d': kp3d, 'kp3d_score': S, 'kp3d_err': E, 'num_cams': num_cams}
+
+
+def run_stage(result_dir, camera_ids, config=None, joint_len=None):
+    """File-to-file form of the 3D stage: the part of step4_aniposefiltering.proc after the 2D
+    filter (:172-339).  Reads ``<result_dir>/kp2d_f.pickle`` (array (F, J, A, 3, C) as written at
+    :169-170), ``calibration.toml`` (:138, loaded like :212-213) and, unless ``config`` is given,
+    ``config.toml`` (:102-104); writes ``kp3d.pickle`` with the reference's dict layout
+    {kp3d (A,F,J,3), kp3d_score (A,F,J), kp3d_err (A,F,J), joint_len} (:332-339) and returns it.
+    ``camera_ids`` is the camera_id list of calib/config.yaml (:107-110, 196-199)."""
+    import os
+    import pickle
+
+    from .cameras import CameraGroup
+
+    with open(os.path.join(result_dir, 'kp2d_f.pickle'), 'rb') as f:
+        kp2d_f = pickle.load(f)
+    if config is None:
+        import toml
+        config = toml.load(os.path.join(result_dir, 'config.toml'))
+    tri = config['triangulation']
+    cgroup = CameraGroup.load(os.path.join(result_dir, 'calibration.toml'))
+    cgroup = cgroup.subset_cameras_names([str(i) for i in camera_ids])
+    kp = np.ascontiguousarray(np.asarray(kp2d_f, dtype=np.float64).transpose((2, 4, 0, 1, 3)))   # (A, C, F, J, 3), :190
+    res = reconstruct(cgroup, kp, score_threshold=tri['score_threshold'], ransac=bool(tri.get('ransac', False)),
+                      optim=bool(tri.get('optim', False)))
+    data = {'kp3d': res['kp3d'], 'kp3d_score': res['kp3d_score'], 'kp3d_err': res['kp3d_err'],
+            'joint_len': [] if joint_len is None else joint_len}
+    with open(os.path.join(result_dir, 'kp3d.pickle'), 'wb') as f:
+        pickle.dump(data, f)
+    return data

@@ -350,3 +350,35 @@ def test_gpu_baseline_full_size_properties():
     assert torch.equal(torch.isnan(xyp[:, :, 0]), ~picked[:, :, 0])
     # selected => error below the acceptance bound; early exit => below the 0.5 px threshold or arg-min
     assert float(rerr[sel].max()) < 200.0
+
+
+def test_gpu_step4_file_stage(tmp_path):
+    """pipeline3d.run_stage: kp2d_f.pickle + calibration.toml + config -> kp3d.pickle with the
+    reference's layout (step4_aniposefiltering.py:172-339), checked against the oracle."""
+    import pickle
+    from macaque_3d_pose_estimation_b200 import pipeline3d
+    seed = 9
+    dicts = synth.make_rig(8, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    CameraGroup.from_dicts(dicts).dump(str(tmp_path / "calibration.toml"))
+    A, F, J = 2, 25, 17
+    X = synth.make_tracks(F, A, seed=seed)
+    p2 = synth.corrupt(og.project(cams, X.reshape(-1, 3)), seed=seed).reshape(8, F, A, J, 2)
+    sc = np.random.default_rng(seed).uniform(0.3, 1.0, size=(8, F, A, J))
+    ids = [8, 7, 6, 5, 4, 3, 2, 1]                      # camera order of calib/config.yaml, not of the toml
+    order = [i - 1 for i in ids]                        # the data's camera axis follows that order (step4:196-213)
+    kp2d_f = np.concatenate([p2[order], sc[order][..., None]], axis=-1).transpose(1, 3, 2, 4, 0)   # (F, J, A, 3, C)
+    with open(tmp_path / "kp2d_f.pickle", "wb") as f:
+        pickle.dump(kp2d_f, f)
+    cfg = {"triangulation": {"score_threshold": 0.5, "ransac": False, "optim": False}}
+    data = pipeline3d.run_stage(str(tmp_path), ids, config=cfg)
+    with open(tmp_path / "kp3d.pickle", "rb") as f:
+        disk = pickle.load(f)
+    assert set(disk) == {"kp3d", "kp3d_score", "kp3d_err", "joint_len"}
+    assert disk["kp3d"].shape == (A, F, J, 3) and disk["kp3d_score"].shape == (A, F, J)
+    for a in range(A):
+        pts = p2[order][:, :, a].copy()
+        pts[sc[order][:, :, a] < 0.5] = np.nan
+        ref = og.triangulate([cams[i] for i in order], pts.reshape(8, F * J, 2)).reshape(F, J, 3)
+        assert _eq_nan(disk["kp3d"][a], ref) and np.nanmax(np.abs(disk["kp3d"][a] - ref)) <= P3D_TOL_MM
+    assert np.array_equal(data["kp3d"], disk["kp3d"], equal_nan=True)

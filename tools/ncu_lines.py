@@ -77,7 +77,9 @@ def main():
     print("%-22s %6s %10s %8s %8s" % ("file:line", "%inst", "warp/pt", "thr/pt", "%samples"))
     order = -2 if "--by-samples" in sys.argv else -1
     srt = sorted(agg.items(), key=(lambda kv: -kv[1][2]) if "--by-samples" in sys.argv else (lambda kv: -kv[1][0]))
-    for key, v in srt[:60]:
+    if "--all" in sys.argv:
+        srt = sorted(agg.items(), key=lambda kv: (kv[0][0], kv[0][1]))
+    for key, v in (srt if "--all" in sys.argv else srt[:60]):
         top = ",".join("%s:%d" % kv for kv in v[3].most_common(3))
         print("%-22s %6.2f %10.1f %8.0f %8.2f  %s" % ("%s:%d" % key, 100.0 * v[0] / tot, v[0] / npts, v[1] / npts,
                                                       100.0 * v[2] / max(tots, 1), top))
