@@ -14,7 +14,8 @@
 //                   planes, coalesced), solve the full set (s = 0), rank the cameras by
 //                   their residual there ("suspicion order"), write the per-point slot.
 //                   ~20 % of the points are decided here.
-//   k_ransac_search persistent warps; a GROUP of GS = 16 lanes (>= cameras) =
+//   k_ransac_search (rigs of 9..16 cameras; rigs of <= 8 cameras use k_ransac_search8,
+//                   m3d_ransac8.cuh)  persistent warps; a GROUP of GS = 16 lanes (>= cameras) =
 //                   one point, lane = subset (GS consecutive s per step), 32 / GS points in
 //                   flight per warp; idle groups take the next undecided point of the
 //                   warp's current 32-point batch, batches come from an atomic counter.
