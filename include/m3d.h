@@ -164,6 +164,24 @@ int m3d_match_svt(const double* W_dev, const int32_t* dim_dev, int32_t F, int32_
                   int32_t max_iter, uint8_t* match_dev, int32_t* iters_dev, int32_t device,
                   void* stream);
 
+/* ---- 2D keypoint filter of the step-4 stage ---------------------------------------- */
+/* anipose filter_pose.viterbi_path (src/third_party/anipose/filter_pose.py:48-120, with
+ * remove_dups :26-46 and the score threshold of filter_pose_viterbi :157) for S independent
+ * series of F frames at once; caller: step4_aniposefiltering.py:144-170 (one series per
+ * (animal, camera, joint)).
+ *   cand_dev (S,F,P,3)  x, y, score of the P candidate detections per frame (not modified)
+ *   n_back              frames a detection stays a particle (config n_back, step4: 3)
+ *   thres_dist          scale of the transition model (config offset_threshold, step4: 25)
+ *   score_threshold     candidates with score < threshold are dropped (step4: 0.3)
+ *   dup_thres           candidates within this distance of an earlier one of the same frame
+ *                       are dropped (the reference passes 5)
+ *   out_dev (S,F,3)     chosen particle per frame: x, y, score * 2^-age; (-1,-1,0.001) = missing
+ *   choice_dev (S,F) i32 age * P + candidate index of the choice, -1 = missing   [may be NULL]
+ * Limits: n_back <= 8 and n_back * P <= 32. */
+int m3d_viterbi_filter(const double* cand_dev, int64_t S, int64_t F, int32_t P, int32_t n_back,
+                       double thres_dist, double score_threshold, double dup_thres,
+                       double* out_dev, int32_t* choice_dev, int32_t device, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Number of kernels this library has launched on the calling process (bench.py's
  * gpu_launches). */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "m3d_ray_affinity": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _D, _P, _P, _P]),
     "m3d_triangulate_ls": (ctypes.c_int, [_P, _P, _P, _L, _P, _P]),
     "m3d_match_svt": (ctypes.c_int, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _I, _P, _P, _I, _P]),
+    "m3d_viterbi_filter": (ctypes.c_int, [_P, _L, _L, _I, _I, _D, _D, _D, _P, _P, _I, _P]),
     "m3d_launch_count": (_L, []),
     "m3d_probe_fp64_tflops": (ctypes.c_int, [_I, ctypes.POINTER(_D)]),
 }

@@ -119,3 +119,28 @@ def corrupt(p2d, seed=20261018, noise=0.3, p_outlier=0.0, sigma_outlier=60.0, p_
         m = rng.random((C, N)) < p_missing
         p[m] = np.nan
     return p
+
+
+def make_detection_series(n_frames, n_joints, n_possible, seed, jump=0.05, low=0.1):
+    """Synthetic 2D detections (F, J, P, 3) [x, y, score]: smooth tracks + detector noise, gross
+    jumps, low-score frames; extra candidates are a near duplicate (within 5 px: remove_dups) or a
+    distractor."""
+    rng = np.random.default_rng(seed)
+    F, J, P = n_frames, n_joints, n_possible
+    pos = rng.uniform([300, 300], [1700, 1200], size=(J, 2))[None] + np.cumsum(rng.normal(0, 4.0, size=(F, J, 2)), axis=0)
+    pts = np.zeros((F, J, P, 3))
+    pts[:, :, 0, :2] = pos + rng.normal(0, 0.7, size=(F, J, 2))
+    pts[:, :, 0, 2] = rng.uniform(0.35, 1.0, size=(F, J))
+    jm = rng.random((F, J)) < jump
+    pts[jm, 0, :2] += rng.normal(0, 60.0, size=(int(jm.sum()), 2))
+    lw = rng.random((F, J)) < low
+    pts[lw, 0, 2] = rng.uniform(0.0, 0.29, size=int(lw.sum()))
+    for p in range(1, P):
+        near = rng.random((F, J)) < 0.3
+        pts[:, :, p, :2] = np.where(near[..., None], pts[:, :, 0, :2] + rng.normal(0, 1.5, size=(F, J, 2)),
+                                    pos + rng.normal(0, 40.0, size=(F, J, 2)))
+        pts[:, :, p, 2] = rng.uniform(0.1, 0.9, size=(F, J))
+    # a stretch of missing detections at the start and in the middle of one series
+    pts[:4, 0, :, 2] = 0.05
+    pts[F // 2:F // 2 + 5, min(1, J - 1), :, 2] = 0.05
+    return pts

@@ -9,6 +9,7 @@ to what the reference's own code returns:
   src/third_party/aniposelib/cameras.py  Camera/FisheyeCamera/CameraGroup
   src/pipeline/step2_crossviewmatching.py  geometry_affinity2, matchSVT
   src/utils/multicam_toolbox.py  triangulatePoints
+  src/third_party/anipose/filter_pose.py  viterbi_path, wrap_points
 Each .npz stores the rig (camera dict fields as arrays), the inputs and every
 output, so that nothing under /root/reference is needed at test time.
 """
@@ -222,6 +223,37 @@ def case_crossview(ref, name, n_frames, seed, drop=0.0):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
 
 
+viterbi_series = synth.make_detection_series
+
+
+def case_viterbi(name, n_frames, n_joints, n_possible, seed, score_threshold=0.3, n_back=3, offset_threshold=25):
+    """anipose/filter_pose.py viterbi_path executed per series exactly as filter_pose_viterbi
+    :151-186 does (score threshold written into the input, one series per joint; the spawn Pool of
+    the reference only distributes these independent calls)."""
+    import src.third_party.aniposelib as al
+    import src.third_party.aniposelib.boards  # noqa: F401
+    sys.modules.setdefault("aniposelib", al)
+    sys.modules.setdefault("aniposelib.boards", al.boards)
+    from src.third_party.anipose import filter_pose as fp
+    all_points = viterbi_series(n_frames, n_joints, n_possible, seed)
+    inp = all_points.copy()
+    points_full = all_points[:, :, :, :2]
+    scores_full = all_points[:, :, :, 2]
+    points_full[scores_full < score_threshold] = np.nan
+    F, J = n_frames, n_joints
+    points = np.full((F, J, 2), np.nan)
+    scores = np.empty((F, J))
+    t0 = time.time()
+    for j in range(J):
+        points[:, j], scores[:, j] = fp.viterbi_path(points_full[:, j, :], scores_full[:, j], n_back, offset_threshold)
+    dt = time.time() - t0
+    wrapped = fp.wrap_points(points, scores)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), all_points=inp, points=points, scores=scores,
+                        wrapped=wrapped, score_threshold=score_threshold, n_back=n_back,
+                        offset_threshold=offset_threshold, ref_seconds=dt)
+    print("%-28s F=%d J=%d P=%d  reference %.2f s" % (name, F, J, n_possible, dt))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -254,6 +286,9 @@ def main():
                                                 noise=0.55, p_outlier=0.1, p_missing=0.1),
         "crossview_m48": lambda: case_crossview(ref, "crossview_m48", 4, S + 21),
         "crossview_ragged": lambda: case_crossview(ref, "crossview_ragged", 3, S + 22, drop=0.15),
+        "viterbi_p1": lambda: case_viterbi("viterbi_p1", 400, 6, 1, S + 31),
+        "viterbi_p2": lambda: case_viterbi("viterbi_p2", 150, 4, 2, S + 32),
+        "viterbi_p1_nb4": lambda: case_viterbi("viterbi_p1_nb4", 120, 3, 1, S + 33, n_back=4, offset_threshold=10),
     }
     for name, fn in cases.items():
         if args.only and args.only != name:

@@ -88,6 +88,15 @@ def main():
     blocks = match.reshape(F, C, A, C, A)
     diag = torch.diagonal(blocks, dim1=2, dim2=4)               # same animal across cameras
     out["k_match_svt (M=48)"]["same_animal_link_rate"] = float(diag.double().mean().item())
+    # 2D Viterbi filter (step-4 stage): 8 animals x 16 cameras x 17 joints = 2176 series
+    from macaque_3d_pose_estimation_b200 import filter2d
+    Sv, Fv = 2176, 20000
+    det = torch.from_numpy(np.ascontiguousarray(
+        synth.make_detection_series(Fv, 64, 1, 5).transpose(1, 0, 2, 3))).to(dev).repeat(Sv // 64, 1, 1, 1).contiguous()
+    rec("k_viterbi (P=1, n_back=3, 2176 series)",
+        timeit(lambda: filter2d.viterbi_series(det, 3, 25.0, 0.3), reps=3), 24 + 24, Sv * Fv, "series-frames")
+    if "--only-viterbi" in sys.argv:
+        out = {k: v for k, v in out.items() if "viterbi" in k}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kernel_bench.json"), "w"), indent=1)
 
