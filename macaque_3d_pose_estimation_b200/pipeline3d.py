@@ -3,8 +3,9 @@ on the GPU CameraGroup: score gating -> triangulate / triangulate_ransac ->
 reprojection error -> per-joint score and error arrays.
 
 All animals are reconstructed in ONE kernel call (the reference loops over animals and
-points in Python, step4:219, cameras.py:628/683); file I/O, calibration assembly and the
-Viterbi filter around it are unchanged reference territory and not reimplemented here.
+points in Python, step4:219, cameras.py:628/683).  ``run_filter_stage`` / ``run_stage`` /
+``run_step4`` are the file-to-file forms (kp2d.pickle -> kp2d_f.pickle -> kp3d.pickle); the
+calibration assembly from the lab's HDF5 files (step4:101-138) stays reference territory.
 The ``optim=True`` branch (CameraGroup.optim_points, step4:228-291) is outside the
 accelerated path.
 """
@@ -84,3 +85,28 @@ def run_stage(result_dir, camera_ids, config=None, joint_len=None):
     with open(os.path.join(result_dir, 'kp3d.pickle'), 'wb') as f:
         pickle.dump(data, f)
     return data
+
+
+def run_filter_stage(result_dir):
+    """File-to-file form of the 2D filter of step4_aniposefiltering.proc (:140-170): reads
+    ``kp2d.pickle`` (array (A, F, C, J, 3)), runs the Viterbi filter with the constants of
+    :146-150 on every (animal, camera, joint) series in one launch, writes ``kp2d_f.pickle``
+    ((F, J, A, 3, C)) and returns it."""
+    import os
+    import pickle
+
+    from . import filter2d
+
+    with open(os.path.join(result_dir, 'kp2d.pickle'), 'rb') as f:
+        kp2d = pickle.load(f)
+    kp2d_f = filter2d.filter_stage(kp2d)
+    with open(os.path.join(result_dir, 'kp2d_f.pickle'), 'wb') as f:
+        pickle.dump(kp2d_f, f)
+    return kp2d_f
+
+
+def run_step4(result_dir, camera_ids, config=None, joint_len=None):
+    """kp2d.pickle + calibration.toml (+ config.toml) -> kp2d_f.pickle, kp3d.pickle: everything of
+    step4_aniposefiltering.proc after the calibration assembly (:140-339)."""
+    run_filter_stage(result_dir)
+    return run_stage(result_dir, camera_ids, config=config, joint_len=joint_len)

@@ -117,3 +117,37 @@ def test_gpu_step4_filter_stage_layout():
             ref[:, :, a, :, c] = np.squeeze(ov.wrap_points(pf, sf))
     assert got.shape == ref.shape == (F, J, A, 3, C)
     assert np.array_equal(got, ref, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gpu_step4_files_end_to_end(tmp_path):
+    """pipeline3d.run_step4: kp2d.pickle -> kp2d_f.pickle -> kp3d.pickle (step4:140-339)."""
+    import pickle
+    from macaque_3d_pose_estimation_b200 import filter2d, pipeline3d, synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    seed, A, F, J, C = 21, 2, 60, 17, 8
+    dicts = synth.make_rig(C, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    CameraGroup.from_dicts(dicts).dump(str(tmp_path / "calibration.toml"))
+    X = synth.make_tracks(F, A, seed=seed)                                       # (F, A, J, 3)
+    p2 = synth.corrupt(og.project(cams, X.reshape(-1, 3)), seed=seed).reshape(C, F, A, J, 2)
+    sc = np.random.default_rng(seed).uniform(0.2, 1.0, size=(C, F, A, J))
+    kp2d = np.concatenate([p2, sc[..., None]], axis=-1).transpose(2, 1, 0, 3, 4)   # (A, F, C, J, 3)
+    with open(tmp_path / "kp2d.pickle", "wb") as f:
+        pickle.dump(kp2d, f)
+    cfg = {"triangulation": {"score_threshold": 0.5, "ransac": False, "optim": False}}
+    data = pipeline3d.run_step4(str(tmp_path), list(range(1, C + 1)), config=cfg)
+    with open(tmp_path / "kp2d_f.pickle", "rb") as f:
+        kp2d_f = pickle.load(f)
+    assert kp2d_f.shape == (F, J, A, 3, C)
+    assert np.array_equal(kp2d_f, filter2d.filter_stage(kp2d), equal_nan=True)
+    # 3D stage on the filtered detections == oracle triangulation of the same detections
+    kf = kp2d_f.transpose((2, 4, 0, 1, 3))                                       # (A, C, F, J, 3)
+    for a in range(A):
+        pts = kf[a, :, :, :, :2].copy()
+        pts[kf[a, :, :, :, 2] < 0.5] = np.nan
+        ref = og.triangulate(cams, pts.reshape(C, F * J, 2)).reshape(F, J, 3)
+        assert np.array_equal(np.isnan(data["kp3d"][a]), np.isnan(ref))
+        assert np.nanmax(np.abs(data["kp3d"][a] - ref)) <= 1e-6
