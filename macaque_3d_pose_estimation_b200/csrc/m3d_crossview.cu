@@ -216,14 +216,35 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
     __syncthreads();
     double mu = mu0;
     int it = 0;
+#ifdef M3D_DEBUG_SWEEPS
+    int dbg_sweeps = 0;
+#endif
     for (it = 0; it < max_iter; ++it) {
-      // B = Y/mu + X (column j of the iterate in B[j]), V = I
-      for (int e = tid; e < ne * ne; e += SVT_THREADS) {
-        const int j = e / ne, i = e % ne;
-        double a = 0.0;
-        if (i < n && j < n) a = Y[i * n + j] / mu + X[i * n + j];
-        B[j * ld + i] = a;
-        V[j * ld + i] = (i == j) ? 1.0 : 0.0;
+      // A = Y/mu + X.  First iteration: B = A (column j of the iterate in B[j]), V = I.  Later
+      // iterations warm-start the Jacobi process from the previous iteration's rotations:
+      // B = A V with V kept — the columns of A V are already nearly orthogonal (the ADMM iterate
+      // moves little), so 2-3 sweeps replace ~9 from the identity.
+      if (it == 0) {
+        for (int e = tid; e < ne * ne; e += SVT_THREADS) {
+          const int j = e / ne, i = e % ne;
+          double a = 0.0;
+          if (i < n && j < n) a = Y[i * n + j] / mu + X[i * n + j];
+          B[j * ld + i] = a;
+          V[j * ld + i] = (i == j) ? 1.0 : 0.0;
+        }
+      } else {
+        for (int e = tid; e < n * n; e += SVT_THREADS) Q[e] = Y[e] / mu + X[e];  // Q is free here
+        __syncthreads();
+        for (int e = tid; e < ne * ne; e += SVT_THREADS) {
+          const int j = e / ne, i = e % ne;
+          double a = 0.0;
+          if (i < n) {
+            const double* ar = Q + (size_t)i * n;
+            const double* vj = V + (size_t)j * ld;
+            for (int k = 0; k < n; ++k) a += ar[k] * vj[k];
+          }
+          B[j * ld + i] = a;
+        }
       }
       for (int e = tid; e < n * n; e += SVT_THREADS) X0[e] = X[e];
       __syncthreads();
@@ -256,10 +277,11 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
               bb += __shfl_xor_sync(gmask, bb, off, 32);
               ab += __shfl_xor_sync(gmask, ab, off, 32);
             }
-            if (fabs(ab) > 1e-15 * sqrt(aa * bb) && ab != 0.0) {
-              const double zeta = (bb - aa) / (2.0 * ab);
-              const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-              const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            // rotate when |ab| > 1e-15 sqrt(aa bb); MUFU-seeded reciprocal / sqrt (m3d_math.cuh)
+            if (ab * ab > 1e-30 * (aa * bb) && fabs(ab) > 1e-290) {
+              const double zeta = (bb - aa) * rcp(2.0 * ab);
+              const double t = (zeta >= 0.0 ? 1.0 : -1.0) * rcp(fabs(zeta) + sqrt_fast(1.0 + zeta * zeta));
+              const double cs = rcp(sqrt_fast(1.0 + t * t)), sn = cs * t;
               double* vp = V + (size_t)p * ld;
               double* vq = V + (size_t)q * ld;
               for (int i = sub; i < ne; i += g) {
@@ -277,6 +299,9 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
         }
         const int rotated = *flag;
         __syncthreads();
+#ifdef M3D_DEBUG_SWEEPS
+        ++dbg_sweeps;
+#endif
         if (!rotated) break;
       }
       // shrink weights  max(s_j - lambda/mu, 0) / s_j
@@ -342,7 +367,11 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
       const double xs = (X[i * n + j] + X[j * n + i]) / 2.0;
       out[i * M + j] = xs > 0.5 ? 1 : 0;
     }
+#ifdef M3D_DEBUG_SWEEPS
+    if (iters && tid == 0) iters[f] = dbg_sweeps;
+#else
     if (iters && tid == 0) iters[f] = it < max_iter ? it : max_iter - 1;
+#endif
     __syncthreads();
   }
 }

@@ -285,6 +285,7 @@ k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ 
 // ---------------------------------------------------------------------------------------
 #include "m3d_ransac.cuh"
 #include "m3d_ransac8.cuh"
+#include "m3d_ransac16.cuh"
 
 // ---------------------------------------------------------------------------------------
 // fp64 FMA peak probe (the second roofline of this path)
@@ -585,8 +586,6 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
                          cudaStream_t st) {
   const int C = rig->dev.n_cams;
   const int sms = sm_count_of(rig->device);
-  const int GSv = 16;  // lanes per point in k_ransac_search (>= cameras)
-  const size_t smem = ransac_smem_bytes(C > 0 ? C : 1, GSv);
   const int64_t chunk = N < kRansacChunk ? N : kRansacChunk;
   const bool small_rig = C <= 8;  // table-driven search on per-point records (m3d_ransac8.cuh)
   double* U = nullptr;
@@ -629,24 +628,6 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
       rc = fail(M3D_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
       break;
     }
-#define CALLB(F, P, GSZ, MB)                                                                              \
-  do {                                                                                                    \
-    auto kfn = k_ransac_search<F, P, GSZ, MB>;                                                            \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    int per_sm = 0;                                                                                       \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RANSAC_THREADS, smem);                    \
-    if (per_sm < 1) per_sm = 1;                                                                           \
-    int64_t blocks = (int64_t)sms * per_sm;                                                               \
-    const int64_t need = (n + 32 * RANSAC_WARPS - 1) / (32 * RANSAC_WARPS);                               \
-    if (blocks > need) blocks = need;                                                                     \
-    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,    \
-                                                        init_best, U, slots, counter);                    \
-  } while (0)
-    // measured on B200: 128 registers (4 CTAs / SM) beats every tighter cap (spills) and a
-    // larger shared-memory carve-out (smaller L1 for the spill traffic)
-    // measured on B200 (8 cameras): groups of 8 / 16 / 32 lanes run within 3 % of each other
-    // (3.69 / 3.80 / 3.66e8 inst/s) — the kernel is bound by dependent fp64 latency at 16
-    // warps / SM (128 registers), not by lane utilisation; tighter register caps spill and lose.
 #define CALLC(F, P, MB)                                                                                   \
   do {                                                                                                    \
     auto kfn = k_ransac_search8<F, P, MB>;                                                                \
@@ -660,21 +641,37 @@ static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int un
     kfn<<<(unsigned)blocks, RANSAC_THREADS, smem8, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,   \
                                                          init_best, U, slots, counter);                   \
   } while (0)
-    // rigs of at most 8 cameras: table-driven search (m3d_ransac8.cuh); larger rigs: generic kernel.
+#define CALLD(F, P, MB)                                                                                   \
+  do {                                                                                                    \
+    auto kfn = k_ransac_search16<F, P, MB>;                                                               \
+    const size_t smem16 = ransac16_smem_bytes();                                                          \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);                  \
+    int per_sm = 0;                                                                                       \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RANSAC_THREADS, smem16);                  \
+    if (per_sm < 1) per_sm = 1;                                                                           \
+    int64_t blocks = (int64_t)sms * per_sm;                                                               \
+    const int64_t need = (n + 32 * RANSAC_WARPS - 1) / (32 * RANSAC_WARPS);                               \
+    if (blocks > need) blocks = need;                                                                     \
+    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem16, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,  \
+                                                          init_best, U, slots, counter);                  \
+  } while (0)
+    // rigs of at most 8 cameras: k_ransac_search8; 9..16 cameras: k_ransac_search16 (one more table
+    // level; 16 warps / SM at 128 registers, 52 KB shared memory per CTA).
     // measured on B200 (cfg 3): 16 / 20 / 24 / 32 warps per SM (128 / 96 / 80 / 64 registers) run at
     // 4.27 / 4.2 / 4.58 / 4.50e8 inst/s — 24 warps is the default, M3D_RANSAC_VARIANT=4|8 the others
     static const int dev_variant = [] { const char* e = getenv("M3D_RANSAC_VARIANT"); return e ? atoi(e) : 0; }();
 #define CALL(F, P)                                   \
   do {                                               \
-    if (!small_rig) CALLB(F, P, 16, 4);              \
+    if (!small_rig && dev_variant == 3) CALLD(F, P, 3); \
+    else if (!small_rig) CALLD(F, P, 4);             \
     else if (dev_variant == 4) CALLC(F, P, 4);       \
     else if (dev_variant == 8) CALLC(F, P, 8);       \
     else CALLC(F, P, 6);                             \
   } while (0)
     M3D_DISPATCH_MODEL(rig, CALL);
 #undef CALL
-#undef CALLB
 #undef CALLC
+#undef CALLD
     rc = check_launch("k_ransac_search");
     if (rc) break;
     k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
