@@ -133,16 +133,17 @@ def test_gpu_ransac_golden(name):
     (5, "pinhole", dict(p_outlier=0.3, p_missing=0.1)),
     (2, "pinhole", dict(p_outlier=0.1, p_missing=0.1)),
     (11, "pinhole", dict(p_outlier=0.1, p_missing=0.1)),
+    (16, "pinhole", dict(p_outlier=0.05, p_missing=0.3)),      # all three table levels of k_ransac_search16
 ])
 def test_gpu_ransac_random_vs_oracle(n_cams, model, kw):
     seed = 777 + n_cams
     dicts = synth.make_rig(n_cams, model, seed=seed)
     cams = fixtures.cams_from_dicts(dicts)
     cg = CameraGroup.from_dicts(dicts)
-    n_frames = 8 if n_cams > 8 else 60
+    n_frames = 2 if n_cams >= 16 else (8 if n_cams > 8 else 60)
     X = synth.make_tracks(n_frames, 4, seed=seed).reshape(-1, 3)
     p2 = synth.corrupt(og.project(cams, X), seed=seed, **kw)
-    for mc in (2, 3):
+    for mc in ((2,) if n_cams >= 16 else (2, 3)):               # the oracle needs ~20 s per 100 16-camera points
         o = og.triangulate_ransac(cams, p2, min_cams=mc, return_stats=True)
         h = cg.triangulate_ransac(p2, min_cams=mc, return_stats=True)
         assert np.array_equal(o[1], h[1])
