@@ -6,6 +6,7 @@
 //                    ADMM iterate and a one-sided Jacobi SVD of it held in shared memory.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/m3d.h"
@@ -199,6 +200,8 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
     }
     const int ne = n + (n & 1);  // even size for the tournament schedule (dummy column = n)
     const int npairs = ne / 2;
+    // lanes per column pair: as many as fit (the round is latency-bound: measured 35.6e3 frames/s
+    // with 8 lanes per pair at M = 48, 24.4e3 with 4)
     int g = 32;
     while (g > 1 && g * npairs > SVT_THREADS) g >>= 1;
     const int pair_of = tid / g, sub = tid % g;
@@ -260,8 +263,10 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
               p = ne - 1;
               q = r;
             } else {
-              p = (r + pair_of) % (ne - 1);
-              q = (r - pair_of + (ne - 1)) % (ne - 1);
+              p = r + pair_of;  // (r + pair_of) mod (ne - 1), pair_of < ne / 2
+              if (p >= ne - 1) p -= ne - 1;
+              q = r - pair_of;
+              if (q < 0) q += ne - 1;
             }
             double* bp = B + (size_t)p * ld;
             double* bq = B + (size_t)q * ld;
@@ -292,7 +297,8 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
                 vp[i] = cs * vx - sn * vy;
                 vq[i] = sn * vx + cs * vy;
               }
-              if (sub == 0) *flag = 1;
+              // bit 0: some rotation; bit 1: one that was not yet in the quadratic end phase
+              if (sub == 0) atomicOr(flag, (ab * ab > 1e-16 * (aa * bb)) ? 3 : 1);
             }
           }
           __syncthreads();
@@ -302,7 +308,9 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
 #ifdef M3D_DEBUG_SWEEPS
         ++dbg_sweeps;
 #endif
-        if (!rotated) break;
+        // no rotation, or only rotations of relative size <= 1e-8: what they leave behind is of
+        // second order (<= 1e-16), the next sweep would not rotate
+        if (!(rotated & 2)) break;
       }
       // shrink weights  max(s_j - lambda/mu, 0) / s_j
       const double tau = lambda / mu;
@@ -416,9 +424,10 @@ int m3d_match_svt(const double* W, const int32_t* dim, int32_t F, int32_t M, int
   const size_t smem = sizeof(double) * (2 * (size_t)ld * (M + 1) + 3 * (size_t)(M + 1) + 64);
   cudaError_t e = cudaFuncSetAttribute(k_match_svt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("k_match_svt smem: ") + cudaGetErrorString(e));
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  static const int cap = [] { const char* e = getenv("M3D_SVT_CTAS"); return e ? atoi(e) : 5; }();
+  if (per_sm > cap) per_sm = cap;
   int grid = sms * per_sm;
   if (grid > F) grid = F;
   double* ws = nullptr;  // per-CTA global scratch: X, X0, Y, Wm, Q
