@@ -126,6 +126,19 @@ int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy_dev, int64_t N,
                            double* xy_picked_dev, double* err_dev, int32_t* subset_dev,
                            int32_t* neval_dev, void* stream);
 
+/* CameraGroup.triangulate_possible with P candidates per camera (cameras.py:639-724): per
+ * point, itertools.product over the cameras that have a valid candidate (ascending), each
+ * offering its valid candidates (ascending) and then "none"; same skip / accept / stop rules
+ * as above.  xy_dev (C,N,P,2) raw pixels (NaN x = no candidate); picked_dev (C,N,P) u8;
+ * xy_picked_dev (C,N,2) the chosen candidates; index_dev (N) i32 position of the accepted
+ * combination in product order, -1 when none; neval_dev (N) i32.  Limit: C * P <= 32.
+ * (The reference only ever calls this with P == 1, which is m3d_triangulate_ransac.) */
+int m3d_triangulate_possible(const m3d_rig* rig, const double* xy_dev, int64_t N, int32_t P,
+                             int32_t undistort, int32_t min_cams, double threshold,
+                             double init_best, double* p3d_dev, uint8_t* picked_dev,
+                             double* xy_picked_dev, double* err_dev, int32_t* index_dev,
+                             int32_t* neval_dev, void* stream);
+
 /* ---- host-buffer pipelines (H2D and D2H inside the call) --------------------------- */
 /* Same results as the _dev calls above; xy_host (C,N,2) etc. live in host memory
  * (page-locked memory gives full PCIe speed; pageable memory works but is slower). */

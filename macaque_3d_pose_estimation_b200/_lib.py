@@ -56,6 +56,7 @@ SIGNATURES = {
     "m3d_reproj_error": (ctypes.c_int, [_P, _P, _P, _L, _I, _P, _P]),
     "m3d_triangulate_error": (ctypes.c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "m3d_triangulate_ransac": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P]),
+    "m3d_triangulate_possible": (ctypes.c_int, [_P, _P, _L, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P]),
     "m3d_triangulate_error_host": (ctypes.c_int, [_P, _P, _L, _I, _P, _P]),
     "m3d_triangulate_ransac_host": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "m3d_host_register": (ctypes.c_int, [_P, _L]),

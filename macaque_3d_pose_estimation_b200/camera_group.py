@@ -158,18 +158,33 @@ class CameraGroup:
 
     def triangulate_possible(self, points, undistort=True, min_cams=2, progress=False,
                              threshold=0.5, return_stats=False):
-        """Given an CxNxPx2 array, triangulate all camera subsets and pick the one with the
-        best reprojection error (cameras.py:639-724).  Implemented for P == 1 (one candidate
-        per camera), which is the only form the reference's callers use
-        (triangulate_ransac, cameras.py:738-743)."""
+        """Given an CxNxPx2 array, triangulate all combinations of one candidate (or none) per
+        camera and pick the one with the best reprojection error (cameras.py:639-724).  P == 1 is
+        the camera-subset search of triangulate_ransac (k_ransac_search8/16); P > 1 runs the
+        mixed-radix product on k_possible (cameras * P <= 32).  Returns (points_3d (N,3),
+        picked_vals (C,N,P) bool, points_2d (C,N,2), errors (N,)); with return_stats also the
+        index of the accepted combination in itertools.product order and the number evaluated."""
         self._assert_cams(points)
         n_cams, n_points, n_possible, _ = points.shape
-        if n_possible != 1:
-            raise NotImplementedError(
-                "triangulate_possible with %d candidates per camera: only P == 1 "
-                "(triangulate_ransac) is on the accelerated path" % n_possible)
-        pts = points.reshape(n_cams, n_points, 2)
-        return self._ransac(pts, undistort, min_cams, threshold, 200.0, return_stats)
+        if n_possible == 1:
+            pts = points.reshape(n_cams, n_points, 2)
+            return self._ransac(pts, undistort, min_cams, threshold, 200.0, return_stats)
+        device, like_torch = self._device_of(points)
+        rig = self._rig(device)
+        x = _to_dev(points, device)
+        p3d = torch.empty((n_points, 3), dtype=torch.float64, device=x.device)
+        picked = torch.empty((n_cams, n_points, n_possible), dtype=torch.uint8, device=x.device)
+        xyp = torch.empty((n_cams, n_points, 2), dtype=torch.float64, device=x.device)
+        err = torch.empty((n_points,), dtype=torch.float64, device=x.device)
+        idx = torch.empty((n_points,), dtype=torch.int32, device=x.device)
+        nev = torch.empty((n_points,), dtype=torch.int32, device=x.device)
+        with torch.cuda.device(device):
+            _lib.check(rig._lib.m3d_triangulate_possible(
+                rig.handle, _ptr(x), n_points, int(n_possible), int(bool(undistort)), int(min_cams),
+                float(threshold), 200.0, _ptr(p3d), _ptr(picked), _ptr(xyp), _ptr(err), _ptr(idx), _ptr(nev),
+                _stream(device)), "m3d_triangulate_possible")
+        res = (p3d, picked.bool(), xyp, err) + ((idx, nev) if return_stats else ())
+        return res if like_torch else tuple(t.cpu().numpy() for t in res)
 
     def triangulate_ransac(self, points, undistort=True, min_cams=2, progress=False,
                            return_stats=False):

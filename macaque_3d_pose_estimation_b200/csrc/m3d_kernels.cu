@@ -286,6 +286,7 @@ k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ 
 #include "m3d_ransac.cuh"
 #include "m3d_ransac8.cuh"
 #include "m3d_ransac16.cuh"
+#include "m3d_possible.cuh"
 
 // ---------------------------------------------------------------------------------------
 // fp64 FMA peak probe (the second roofline of this path)
@@ -694,6 +695,33 @@ int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy, int64_t N, int3
     return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: NULL buffer");
   return launch_ransac(rig, xy, N, undistort, min_cams, threshold, init_best, p3d, picked, xy_picked,
                        err, subset, neval, st);
+}
+
+int m3d_triangulate_possible(const m3d_rig* rig, const double* xy, int64_t N, int32_t P, int32_t undistort,
+                             int32_t min_cams, double threshold, double init_best, double* p3d,
+                             uint8_t* picked, double* xy_picked, double* err, int32_t* index,
+                             int32_t* neval, void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate_possible");
+  const int C = rig->dev.n_cams;
+  if (P < 1 || C * P > POSS_SLOTS)
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: cameras * candidates must be between 1 and 32");
+  if (N == 0) return M3D_OK;
+  if (!p3d || !err || (!xy && C > 0)) return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: NULL buffer");
+  const size_t smem = possible_smem_bytes();
+  int64_t blocks = (N + POSS_WARPS - 1) / POSS_WARPS;
+  const int64_t cap = (int64_t)sms * 8;
+  if (blocks > cap) blocks = cap;
+#define CALL(F, Pm)                                                                                   \
+  do {                                                                                                \
+    auto kfn = k_possible<F, Pm>;                                                                     \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+    kfn<<<(unsigned)blocks, POSS_WARPS * 32, smem, st>>>(rig->dev_g, xy, N, P, undistort, min_cams,   \
+                                                         threshold, init_best, p3d, picked, xy_picked, \
+                                                         err, index, neval);                          \
+  } while (0)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_possible");
 }
 
 int m3d_triangulate_ls(const m3d_rig* rig, const double* xy, const uint8_t* use, int64_t N,

@@ -231,6 +231,66 @@ def triangulate_ransac(cams, points, undistort=True, min_cams=2, threshold=0.5,
     return out, picked, points_2d, errors
 
 
+def triangulate_possible(cams, points, undistort=True, min_cams=2, threshold=0.5, init_best=200.0,
+                         return_stats=False):
+    """CameraGroup.triangulate_possible for P candidates per camera (cameras.py:639-724), in the
+    reference's own loop structure: per point, itertools.product over the cameras that have a
+    valid candidate (ascending), each offering its valid candidates (ascending) and then None.
+
+    Returns (out (N,3), picked (C,N,P) bool, points_2d (C,N,2), errors (N,)) and, with
+    return_stats, (index (N,) of the accepted combination in product order, -1 = none,
+    n_evaluated (N,))."""
+    import itertools
+    points = np.asarray(points, dtype=np.float64)
+    assert points.shape[0] == len(cams), \
+        "Invalid points shape, first dim should be equal to" \
+        " number of cameras ({}), but shape is {}".format(len(cams), points.shape)
+    C, N, P, _ = points.shape
+    out = np.full((N, 3), np.nan)
+    picked_vals = np.zeros((C, N, P), dtype=bool)
+    errors = np.zeros(N)
+    points_2d = np.full((C, N, 2), np.nan)
+    index = np.full(N, -1, dtype=np.int64)
+    n_eval = np.zeros(N, dtype=np.int64)
+    for n in range(N):
+        options = []
+        for c in range(C):
+            cand = [(c, x) for x in range(P) if not np.isnan(points[c, n, x, 0])]      # :658-671
+            if cand:
+                options.append(cand + [None])
+        n_cams_max = len(options)
+        best_error, best = float(init_best), None
+        for ix, combo in enumerate(itertools.product(*options)):
+            pk = [q for q in combo if q is not None]
+            if len(pk) < min_cams and len(pk) != n_cams_max:                           # :691
+                continue
+            n_eval[n] += 1
+            cn = [q[0] for q in pk]
+            xn = [q[1] for q in pk]
+            pts = points[cn, n, xn] if pk else np.zeros((0, 2))
+            sub = [cams[c] for c in cn]
+            with np.errstate(all="ignore"):
+                p3d = triangulate(sub, pts[:, None, :], undistort=undistort)[0] if len(pk) else np.full(3, np.nan)
+                err = reprojection_error(sub, p3d[None], pts[:, None, :], mean=True)[0] if len(pk) else np.nan
+            if err < best_error:                                                       # :703
+                best = (p3d, pts, pk, err, ix)
+                best_error = err
+                if best_error < threshold:                                             # :712
+                    break
+        if best is not None:
+            p3d, pts, pk, err, ix = best
+            out[n] = p3d
+            cn = [q[0] for q in pk]
+            xn = [q[1] for q in pk]
+            picked_vals[cn, n, xn] = True
+            errors[n] = err
+            points_2d[cn, n] = pts
+            index[n] = ix
+    if return_stats:
+        return out, picked_vals, points_2d, errors, index, n_eval
+    return out, picked_vals, points_2d, errors
+
+
 # ----------------------------------------------------------------------------
 # loop-faithful port (CPU baseline: same call structure as the reference)
 # ----------------------------------------------------------------------------

@@ -223,6 +223,35 @@ def case_crossview(ref, name, n_frames, seed, drop=0.0):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
 
 
+def case_possible(ref, name, n_cams, n_frames, seed, n_possible=2, min_cams=2, p_swap=0.3, p_missing=0.2):
+    """CameraGroup.triangulate_possible with P candidates per camera (cameras.py:639-724): the
+    second candidate is a distractor (N(0, 40 px) away) or missing; in 30 % of the (camera, point)
+    cells the true detection is the SECOND candidate."""
+    cams = synth.make_rig(n_cams, "pinhole", seed=seed)
+    cg = ref.CameraGroup.from_dicts(cams)
+    rng = np.random.default_rng(seed + 5)
+    X = synth.make_tracks(n_frames, 1, seed=seed).reshape(-1, 3)
+    clean = cg.project(X).reshape(n_cams, -1, 2)
+    N = clean.shape[1]
+    pts = np.full((n_cams, N, n_possible, 2), np.nan)
+    good = clean + rng.normal(0, 0.3, size=clean.shape)
+    for p in range(n_possible):
+        pts[:, :, p] = clean + rng.normal(0, 40.0, size=clean.shape)
+    first = rng.random((n_cams, N)) >= p_swap
+    pts[:, :, 0][first] = good[first]
+    pts[:, :, 1][~first] = good[~first]
+    miss = rng.random((n_cams, N, n_possible)) < p_missing
+    pts[miss] = np.nan
+    pts[:, 0] = np.nan                                   # a point without any candidate
+    pts[1:, 1] = np.nan                                  # a point seen by one camera only
+    t0 = time.time()
+    out, picked, p2d, err = cg.triangulate_possible(pts.copy(), min_cams=min_cams)
+    dt = time.time() - t0
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), points=pts, out=out, picked=picked, points_2d=p2d,
+                        errors=err, min_cams=min_cams, ref_seconds=dt, **rig_arrays(cams))
+    print("%-28s C=%d N=%d P=%d  reference %.2f s" % (name, n_cams, N, n_possible, dt))
+
+
 viterbi_series = synth.make_detection_series
 
 
@@ -286,6 +315,9 @@ def main():
                                                 noise=0.55, p_outlier=0.1, p_missing=0.1),
         "crossview_m48": lambda: case_crossview(ref, "crossview_m48", 4, S + 21),
         "crossview_ragged": lambda: case_crossview(ref, "crossview_ragged", 3, S + 22, drop=0.15),
+        "possible_c4_p2": lambda: case_possible(ref, "possible_c4_p2", 4, 3, S + 41),
+        "possible_c5_p2_min3": lambda: case_possible(ref, "possible_c5_p2_min3", 5, 2, S + 42, min_cams=3),
+        "possible_c3_p3": lambda: case_possible(ref, "possible_c3_p3", 3, 3, S + 43, n_possible=3),
         "viterbi_p1": lambda: case_viterbi("viterbi_p1", 400, 6, 1, S + 31),
         "viterbi_p2": lambda: case_viterbi("viterbi_p2", 150, 4, 2, S + 32),
         "viterbi_p1_nb4": lambda: case_viterbi("viterbi_p1_nb4", 120, 3, 1, S + 33, n_back=4, offset_threshold=10),

@@ -383,3 +383,52 @@ def test_gpu_step4_file_stage(tmp_path):
         ref = og.triangulate([cams[i] for i in order], pts.reshape(8, F * J, 2)).reshape(F, J, 3)
         assert _eq_nan(disk["kp3d"][a], ref) and np.nanmax(np.abs(disk["kp3d"][a] - ref)) <= P3D_TOL_MM
     assert np.array_equal(data["kp3d"], disk["kp3d"], equal_nan=True)
+
+
+POSSIBLE = fixtures.golden_names("possible")
+
+
+@pytest.mark.parametrize("name", POSSIBLE)
+def test_gpu_triangulate_possible_golden(name):
+    """CameraGroup.triangulate_possible with P > 1 candidates per camera (cameras.py:639-724)
+    against golden vectors produced by executing the reference."""
+    g, cams = fixtures.load_golden(name)
+    cg = group_from_golden(g)
+    mc = int(g["min_cams"])
+    out, picked, p2d, err, idx, nev = cg.triangulate_possible(g["points"], min_cams=mc, return_stats=True)
+    assert picked.shape == g["picked"].shape and picked.dtype == np.bool_
+    assert np.array_equal(picked, g["picked"])
+    assert np.array_equal(p2d, g["points_2d"], equal_nan=True)
+    assert _eq_nan(out, g["out"]) and np.nanmax(np.abs(out - g["out"]), initial=0.0) <= P3D_TOL_MM
+    assert np.abs(err - g["errors"]).max() <= ERR_TOL_PX
+    o = og.triangulate_possible(cams, g["points"], min_cams=mc, return_stats=True)
+    assert np.array_equal(idx, o[4]) and np.array_equal(nev, o[5])
+
+
+@pytest.mark.parametrize("C,P,mc", [(8, 2, 2), (6, 3, 3), (16, 2, 2), (8, 4, 2)])
+def test_gpu_triangulate_possible_random_vs_oracle(C, P, mc):
+    seed = 4100 + 10 * C + P
+    dicts = synth.make_rig(C, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    rng = np.random.default_rng(seed)
+    X = synth.make_tracks(1, 1, seed=seed).reshape(-1, 3) * np.array([0.6, 0.6, 0.5])
+    X = X[:12 if C * P <= 18 else 6]
+    clean = og.project(cams, X)
+    N = clean.shape[1]
+    pts = np.full((C, N, P, 2), np.nan)
+    pts[:, :, 0] = clean + rng.normal(0, 0.3, size=clean.shape)
+    far = rng.random((C, N)) < 0.25                       # the true detection is replaced by a distractor
+    pts[:, :, 0][far] += rng.normal(0, 50.0, size=(int(far.sum()), 2))
+    has2 = rng.random((C, N)) < (0.35 if C <= 8 else 0.12)   # keeps the 16-camera products small
+    pts[:, :, 1][has2] = (clean + rng.normal(0, 30.0, size=clean.shape))[has2]
+    pts[rng.random((C, N, P)) < 0.3] = np.nan
+    o = og.triangulate_possible(cams, pts, min_cams=mc, return_stats=True)
+    h = cg.triangulate_possible(pts, min_cams=mc, return_stats=True)
+    assert np.array_equal(o[1], h[1])
+    assert np.array_equal(o[4], h[4]) and np.array_equal(o[5], h[5])
+    assert np.array_equal(o[2], h[2], equal_nan=True)
+    assert _eq_nan(o[0], h[0]) and np.nanmax(np.abs(o[0] - h[0]), initial=0.0) <= P3D_TOL_MM
+    assert np.abs(o[3] - h[3]).max() <= ERR_TOL_PX
+    with pytest.raises(RuntimeError, match="cameras \\* candidates"):
+        CameraGroup.from_dicts(synth.make_rig(8, "pinhole", seed=1)).triangulate_possible(np.zeros((8, 2, 5, 2)))

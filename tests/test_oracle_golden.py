@@ -125,3 +125,14 @@ def test_oracle_crossview(name):
         ref3 = g["f%d_ls_p3d" % f]
         assert _eq_nan(p3, ref3)
         assert np.nanmax(np.abs(p3 - ref3)) <= 1e-7
+
+
+@pytest.mark.parametrize("name", fixtures.golden_names("possible"))
+def test_oracle_triangulate_possible(name):
+    """triangulate_possible with P > 1 candidates per camera (cameras.py:639-724)."""
+    g, cams = fixtures.load_golden(name)
+    out, picked, p2d, err = og.triangulate_possible(cams, g["points"], min_cams=int(g["min_cams"]))
+    assert np.array_equal(picked, g["picked"])
+    assert np.array_equal(p2d, g["points_2d"], equal_nan=True)
+    assert _eq_nan(out, g["out"]) and np.nanmax(np.abs(out - g["out"]), initial=0.0) <= 1e-8
+    assert np.abs(err - g["errors"]).max() <= 1e-10
