@@ -456,6 +456,30 @@ def run_gpu(args):
                 "roofline_frac_hbm": 296 * Nr / (rms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_instance": 296}
         except Exception as ex:  # pragma: no cover
             extra["ransac"] = {"error": str(ex)[:200]}
+        # ---- step-4 2D Viterbi filter on the series of the same recording shape ----
+        try:
+            from macaque_3d_pose_estimation_b200 import filter2d
+            Sv, Fv = A * C * J, 20000
+            det = torch.from_numpy(np.ascontiguousarray(
+                synth.make_detection_series(Fv, 32, 1, seed).transpose(1, 0, 2, 3))).to(device)
+            det = det.repeat((Sv + 31) // 32, 1, 1, 1)[:Sv].contiguous()
+            for _ in range(2):
+                filter2d.viterbi_series(det, 3, 25.0, 0.3)
+            torch.cuda.synchronize()
+            v0 = torch.cuda.Event(enable_timing=True)
+            v1 = torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(3):
+                filter2d.viterbi_series(det, 3, 25.0, 0.3)
+            v1.record()
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1) / 3
+            extra["viterbi_filter"] = {
+                "workload": "step-4 2D Viterbi filter (n_back 3, offset_threshold 25, score_threshold 0.3), %d series "
+                            "(animals x cameras x joints) x %d frames" % (Sv, Fv),
+                "value": Sv * Fv / (vms * 1e-3), "unit": "series-frames/s (one GPU)", "ms_per_step": vms}
+        except Exception as ex:  # pragma: no cover
+            extra["viterbi_filter"] = {"error": str(ex)[:200]}
 
     # ---- CPU baseline: loop-faithful port, one core, bounded sample ---------------------------
     cpu = None
