@@ -432,3 +432,24 @@ def test_gpu_triangulate_possible_random_vs_oracle(C, P, mc):
     assert np.abs(o[3] - h[3]).max() <= ERR_TOL_PX
     with pytest.raises(RuntimeError, match="cameras \\* candidates"):
         CameraGroup.from_dicts(synth.make_rig(8, "pinhole", seed=1)).triangulate_possible(np.zeros((8, 2, 5, 2)))
+
+
+@pytest.mark.parametrize("mc", [1, 4, 6, 7])
+def test_gpu_ransac_min_cams_range(mc):
+    """min_cams from 1 (single-camera subsets are enumerated but can never be accepted) up to
+    more than the valid views (only the full set is tried, cameras.py:691)."""
+    seed = 6060
+    dicts = synth.make_rig(6, "pinhole", seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    X = synth.make_tracks(40, 2, seed=seed).reshape(-1, 3)
+    p2 = synth.corrupt(og.project(cams, X), seed=seed, p_outlier=0.25, p_missing=0.15)
+    o = og.triangulate_ransac(cams, p2, min_cams=mc, return_stats=True)
+    h = cg.triangulate_ransac(p2, min_cams=mc, return_stats=True)
+    assert np.array_equal(o[1], h[1]) and np.array_equal(o[4], h[4]) and np.array_equal(o[5], h[5])
+    assert np.array_equal(o[2], h[2], equal_nan=True)
+    assert np.nanmax(np.abs(o[0] - h[0]), initial=0.0) <= P3D_TOL_MM and np.abs(o[3] - h[3]).max() <= ERR_TOL_PX
+    # a custom threshold goes through triangulate_possible (P = 1)
+    o2 = og.triangulate_ransac(cams, p2, min_cams=mc, threshold=1.5, return_stats=True)
+    h2 = cg.triangulate_possible(p2[:, :, None, :], min_cams=mc, threshold=1.5, return_stats=True)
+    assert np.array_equal(o2[1], h2[1]) and np.array_equal(o2[4], h2[4]) and np.array_equal(o2[5], h2[5])
