@@ -28,71 +28,6 @@ inline size_t ransac8_smem_bytes() {
   return ransac_rig_bytes() + (size_t)(R8_ZEROS + RANSAC_WARPS * R8_WARP_DOUBLES) * sizeof(double);
 }
 
-// dlt_solve (m3d_math.cuh) for a whole warp: the same Newton / Rayleigh-quotient iteration per
-// lane, but warp-convergent and without per-lane control flow.  A lane that has stopped keeps
-// lam fixed and therefore recomputes identical values (so "converged" can be read off the last
-// trip); lanes without work (active = false) ride along on whatever G they were given.  The rare
-// lanes that leave the fast path (step past the pole lam_min(H), degenerate H, no convergence in
-// 8 trips: ~0.2 % of the solves) are redone by the general dlt_solve, which halves such steps
-// back and ends in the Jacobi eigen-solver.
-__device__ __forceinline__ void dlt_solve_warp(const Gram& G, bool active, double& X, double& Y, double& Z) {
-  constexpr unsigned FULLM = 0xffffffffu;
-  double lam = 0.0;
-  bool done = !active;
-  const double tr = G.h[0] + G.h[3] + G.h[5];
-  const double tol = 1e-7 * rcp(tr * tr);  // lam_min(H - lam I) >= det / tr^2
-  double c00, c01, c02, c11, c12, c22, det, p0, p1, p2, dl;
-  bool pd, crit;
-  const double b = G.h[1], c = G.h[2], e = G.h[4];
-#pragma unroll 1
-  for (int it = 0; it < 8; ++it) {
-    const double a = G.h[0] - lam, d = G.h[3] - lam, f = G.h[5] - lam;
-    c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
-    c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
-    det = a * c00 + b * c01 + c * c02;
-    pd = a > 0.0 && c22 > 0.0 && det > 0.0;  // Sylvester: lam < lam_min(H)
-    p0 = c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2];
-    p1 = c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2];
-    p2 = c02 * G.g[0] + c12 * G.g[1] + c22 * G.g[2];
-    const double q = G.g[0] * p0 + G.g[1] * p1 + G.g[2] * p2;
-    const double pp = p0 * p0 + p1 * p1 + p2 * p2;
-    const double wl = G.w - lam;
-    const double num = wl * det - q;
-    const double iden = rcp(det * det + pp);
-    dl = det * num * iden;
-    crit = fabs(dl) <= tol * det;
-    if (it >= 2 && !crit) {
-      // a step at the rounding-noise level of its own numerator (near-parallel rays) cannot be
-      // improved in fp64 either
-      const double noise = 4e-16 * (fabs(wl) * det + fabs(q)) * det * iden;
-      crit = fabs(dl) <= noise;
-    }
-    const double ln = lam + dl;
-    const bool go = !done && pd && !crit && ln >= 0.0;
-    if (go) lam = ln;
-    done = !go;
-    if (!__any_sync(FULLM, go)) break;
-  }
-  bool ok = active && pd && crit;
-  X = Y = Z = qnan();
-  if (ok) {
-    const double idet = rcp(det);
-    double x0 = -p0 * idet, x1 = -p1 * idet, x2 = -p2 * idet;
-    // first-order update X(lam + dl) = X + dl (H - lam I)^-1 X
-    const double y0 = (c00 * x0 + c01 * x1 + c02 * x2) * idet;
-    const double y1 = (c01 * x0 + c11 * x1 + c12 * x2) * idet;
-    const double y2 = (c02 * x0 + c12 * x1 + c22 * x2) * idet;
-    x0 += dl * y0;
-    x1 += dl * y1;
-    x2 += dl * y2;
-    ok = (x0 == x0);
-    X = x0;
-    Y = x1;
-    Z = x2;
-  }
-  if (active && !ok) dlt_solve(G, X, Y, Z);
-}
-
 template <bool FULL, bool PO, int MINB>
 __global__ void __launch_bounds__(RANSAC_THREADS, MINB)
 k_ransac_search8(const RigDev* __restrict__ rig_g, const double* __restrict__ xy, int64_t ld, int64_t n0,
