@@ -181,6 +181,7 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
   double* sig = V + (size_t)ld * (M + 1);  // [Me] singular values -> shrink weights
   double* red = sig + (M + 1);             // [>=32] reduction scratch
   int* flag = reinterpret_cast<int*>(red + 40);
+  double* nrm = red + 48;                  // [Me] running squared column norms of B
   const int tid = threadIdx.x;
   double* X = wsall + (size_t)blockIdx.x * 5 * M * M;
   double* X0 = X + (size_t)M * M;
@@ -255,6 +256,15 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
       for (int sweep = 0; sweep < 40; ++sweep) {
         if (tid == 0) *flag = 0;
         __syncthreads();
+        // exact squared column norms at the start of every sweep; inside the sweep they follow the
+        // rotations (aa' = aa - t ab, bb' = bb + t ab), so a pair costs ONE dot product
+        for (int j = tid; j < ne; j += SVT_THREADS) {
+          const double* bj = B + (size_t)j * ld;
+          double ss = 0.0;
+          for (int i = 0; i < ne; ++i) ss += bj[i] * bj[i];
+          nrm[j] = ss;
+        }
+        __syncthreads();
         for (int r = 0; r < ne - 1; ++r) {
           const unsigned gmask = __ballot_sync(0xffffffffu, jactive);  // lanes that own a column pair
           if (jactive) {
@@ -268,37 +278,41 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
               q = r - pair_of;
               if (q < 0) q += ne - 1;
             }
-            double* bp = B + (size_t)p * ld;
-            double* bq = B + (size_t)q * ld;
-            double aa = 0.0, bb = 0.0, ab = 0.0;
-            for (int i = sub; i < ne; i += g) {
-              const double x = bp[i], y = bq[i];
-              aa += x * x;
-              bb += y * y;
-              ab += x * y;
+            // 16-byte accesses: lane `sub` of the pair holds elements 2 sub, 2 sub + 1 (+ 2 g k)
+            double2* bp = reinterpret_cast<double2*>(B + (size_t)p * ld);
+            double2* bq = reinterpret_cast<double2*>(B + (size_t)q * ld);
+            const int nh = ne >> 1;
+            double ab = 0.0;
+            for (int i = sub; i < nh; i += g) {
+              const double2 x = bp[i], y = bq[i];
+              ab += x.x * y.x;
+              ab += x.y * y.y;
             }
-            for (int off = g >> 1; off > 0; off >>= 1) {
-              aa += __shfl_xor_sync(gmask, aa, off, 32);
-              bb += __shfl_xor_sync(gmask, bb, off, 32);
-              ab += __shfl_xor_sync(gmask, ab, off, 32);
-            }
+            for (int off = g >> 1; off > 0; off >>= 1) ab += __shfl_xor_sync(gmask, ab, off, 32);
+            double aa = nrm[p], bb = nrm[q];
+            aa = aa > 0.0 ? aa : 0.0;
+            bb = bb > 0.0 ? bb : 0.0;
             // rotate when |ab| > 1e-15 sqrt(aa bb); MUFU-seeded reciprocal / sqrt (m3d_math.cuh)
             if (ab * ab > 1e-30 * (aa * bb) && fabs(ab) > 1e-290) {
               const double zeta = (bb - aa) * rcp(2.0 * ab);
               const double t = (zeta >= 0.0 ? 1.0 : -1.0) * rcp(fabs(zeta) + sqrt_fast(1.0 + zeta * zeta));
               const double cs = rcp(sqrt_fast(1.0 + t * t)), sn = cs * t;
-              double* vp = V + (size_t)p * ld;
-              double* vq = V + (size_t)q * ld;
-              for (int i = sub; i < ne; i += g) {
-                const double x = bp[i], y = bq[i];
-                bp[i] = cs * x - sn * y;
-                bq[i] = sn * x + cs * y;
-                const double vx = vp[i], vy = vq[i];
-                vp[i] = cs * vx - sn * vy;
-                vq[i] = sn * vx + cs * vy;
+              double2* vp = reinterpret_cast<double2*>(V + (size_t)p * ld);
+              double2* vq = reinterpret_cast<double2*>(V + (size_t)q * ld);
+              for (int i = sub; i < nh; i += g) {
+                const double2 x = bp[i], y = bq[i];
+                bp[i] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                bq[i] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                const double2 vx = vp[i], vy = vq[i];
+                vp[i] = make_double2(cs * vx.x - sn * vy.x, cs * vx.y - sn * vy.y);
+                vq[i] = make_double2(sn * vx.x + cs * vy.x, sn * vx.y + cs * vy.y);
               }
-              // bit 0: some rotation; bit 1: one that was not yet in the quadratic end phase
-              if (sub == 0) atomicOr(flag, (ab * ab > 1e-16 * (aa * bb)) ? 3 : 1);
+              if (sub == 0) {
+                nrm[p] = aa - t * ab;
+                nrm[q] = bb + t * ab;
+                // bit 0: some rotation; bit 1: one that was not yet in the quadratic end phase
+                atomicOr(flag, (ab * ab > 1e-16 * (aa * bb)) ? 3 : 1);
+              }
             }
           }
           __syncthreads();
@@ -420,7 +434,7 @@ int m3d_match_svt(const double* W, const int32_t* dim, int32_t F, int32_t M, int
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int ld = (M + 1) | 1;  // odd column stride: conflict-free column access
+  const int ld = (M + 2) & ~1;  // even column stride: 16-byte aligned columns for the double2 accesses of the Jacobi sweeps
   const size_t smem = sizeof(double) * (2 * (size_t)ld * (M + 1) + 3 * (size_t)(M + 1) + 64);
   cudaError_t e = cudaFuncSetAttribute(k_match_svt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("k_match_svt smem: ") + cudaGetErrorString(e));
