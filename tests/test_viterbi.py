@@ -73,7 +73,9 @@ def test_gpu_matches_reference_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("F,J,P,n_back,scale", [(1500, 40, 1, 3, 25.0), (400, 24, 2, 3, 25.0), (300, 16, 3, 2, 12.0),
-                                               (1, 5, 1, 3, 25.0), (2, 5, 2, 3, 25.0), (130, 9, 1, 5, 30.0)])
+                                               (1, 5, 1, 3, 25.0), (2, 5, 2, 3, 25.0), (130, 9, 1, 5, 30.0),
+                                               # k_viterbi_small with several candidates per frame (dedup inside)
+                                               (300, 8, 2, 2, 25.0), (200, 6, 4, 1, 20.0), (97, 3, 3, 1, 25.0)])
 def test_gpu_random_vs_oracle(F, J, P, n_back, scale):
     from macaque_3d_pose_estimation_b200 import filter2d
     allp = _series(F, J, P, 77 + F + P)
