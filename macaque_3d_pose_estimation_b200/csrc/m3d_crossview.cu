@@ -445,7 +445,9 @@ int m3d_match_svt(const double* W, const int32_t* dim, int32_t F, int32_t M, int
   int grid = sms * per_sm;
   if (grid > F) grid = F;
   double* ws = nullptr;  // per-CTA global scratch: X, X0, Y, Wm, Q
-  e = cudaMallocAsync(&ws, sizeof(double) * 5 * (size_t)M * M * grid, st);
+  cudaMemPool_t pool = m3d_scratch_pool(device);
+  e = pool ? cudaMallocFromPoolAsync(&ws, sizeof(double) * 5 * (size_t)M * M * grid, pool, st)
+           : cudaMallocAsync(&ws, sizeof(double) * 5 * (size_t)M * M * grid, st);
   if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("m3d_match_svt workspace: ") + cudaGetErrorString(e));
   k_match_svt<<<grid, SVT_THREADS, smem, st>>>(W, dim, F, M, C, alpha, lambda, mu, tol, max_iter, match, iters, ws, ld);
   int rc = m3d_check_launch("k_match_svt");

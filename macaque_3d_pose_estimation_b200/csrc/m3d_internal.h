@@ -11,6 +11,8 @@
 int m3d_fail(int code, const std::string& msg);
 // counts the launch (m3d_launch_count) and converts cudaGetLastError() into a return code
 int m3d_check_launch(const char* what);
+// private stream-ordered memory pool of a device for scratch buffers (nullptr on failure)
+cudaMemPool_t m3d_scratch_pool(int device);
 // device-side camera record / device index of a rig handle
 const m3d::RigDev* m3d_rig_dev(const m3d_rig* rig);
 

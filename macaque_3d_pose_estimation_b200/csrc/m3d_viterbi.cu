@@ -263,6 +263,8 @@ struct VtSmall {
   unsigned short blk[32 * 4];    // codes of the block
   unsigned short codes[VT_TILE * 4];
   int choice[VT_TILE];
+  double dm[36][4];              // P == 1: dm[4 + f][k - 1] = transition between the candidates of
+                                 // frames f and f - k; rows 0..3 = last four frames of the previous block
 };
 
 __device__ __forceinline__ void vt_particle(const double* __restrict__ cs, int64_t frame, int P, int src, double& x,
@@ -292,6 +294,7 @@ k_viterbi_small(const double* __restrict__ cand, int64_t S, int64_t F, int P, in
   const int NP = n_back * P;  // <= 4
   const double* cs = cand + (size_t)s * F * P * 3;
   unsigned short* cd = codes + (size_t)s * F * NP;
+  const double t_same = viterbi_transition(0.0, 0.0, 0.0, 0.0, scale, log_missing);  // d = 0
   unsigned carry[3] = {0u, 0u, 0u};  // valid masks of frames i0 - 1, i0 - 2, i0 - 3
   double T = neg_inf();              // lane b: score of particle b of the previous frame
   int va = 0;
@@ -361,15 +364,65 @@ k_viterbi_small(const double* __restrict__ cand, int64_t S, int64_t F, int P, in
           vt_particle(cs, i, P, mysrc[b], bx[b], by[b], sc);
           w.ls[lane][b] = log(sc);
         }
+      if (P == 1) {
+        // One candidate per frame: a particle IS the candidate of frame i - age, so the transition of
+        // a pair depends only on the two candidate frames.  Of the (up to) 9 pairs of a frame only
+        // the ones that involve candidate i are new — compute those (<= n_back values) here, the
+        // rest are the neighbouring frames' values (or the d = 0 constant), picked up below.
+        if (vm & 1u) {
+          const double* c = cs + (size_t)i * 3;
+          const double cx = c[0], cy = c[1];
+#pragma unroll
+          for (int k = 1; k <= 3; ++k)
+            if (k <= n_back && i - k >= 0 && (pm[k] & 1u)) {
+              const double* o = cs + (size_t)(i - k) * 3;
+              w.dm[4 + lane][k - 1] = viterbi_transition(o[0], o[1], cx, cy, scale, log_missing);
+            }
+          if (n_back >= 4 && i - 4 >= 0) {  // the fourth frame back is outside the pm[] window: test it here
+            const double* o = cs + (size_t)(i - 4) * 3;
+            double ox = o[0];
+            if (o[2] < score_thr) ox = __longlong_as_double(0x7ff8000000000000LL);
+            if (ox == ox) w.dm[4 + lane][3] = viterbi_transition(o[0], o[1], cx, cy, scale, log_missing);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane < nf) {
       if (i > 0) {
         const int pa = w.cnt[lane];
+        if (P == 1) {
 #pragma unroll 1
-        for (int a = 0; a < pa; ++a) {
-          double ax, ay, asc;
-          vt_particle(cs, i - 1, P, w.src[lane][a], ax, ay, asc);
+          for (int a = 0; a < pa; ++a) {
+            const int sa = w.src[lane][a];  // age of particle a at frame i - 1 (255 = missing)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (b < vb) {
+                const int sb = mysrc[b];
+                double pt = log_missing;
+                if (sa != 255 && sb != 255) {
+                  const int fb = lane - sb, fa = lane - 1 - sa;  // candidate frames relative to i0
+                  pt = (fb == fa) ? t_same : (fb > fa ? w.dm[4 + fb][fb - fa - 1] : w.dm[4 + fa][fa - fb - 1]);
+                }
+                w.tr[lane][b * 4 + a] = pt;
+              }
+          }
+        } else {
+          double bx[4], by[4];
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            if (b < vb) w.tr[lane][b * 4 + a] = viterbi_transition(ax, ay, bx[b], by[b], scale, log_missing);
+            if (b < vb) {
+              double sc;
+              vt_particle(cs, i, P, mysrc[b], bx[b], by[b], sc);
+            }
+#pragma unroll 1
+          for (int a = 0; a < pa; ++a) {
+            double ax, ay, asc;
+            vt_particle(cs, i - 1, P, w.src[lane][a], ax, ay, asc);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (b < vb) w.tr[lane][b * 4 + a] = viterbi_transition(ax, ay, bx[b], by[b], scale, log_missing);
+          }
         }
       }
     }
@@ -404,6 +457,11 @@ k_viterbi_small(const double* __restrict__ cand, int64_t S, int64_t F, int P, in
     __syncwarp();
     for (int q = lane; q < nf * NP; q += 32) cd[(size_t)i0 * NP + q] = w.blk[q];
     // carry to the next block
+    if (P == 1 && lane < 16) {
+      const double v = w.dm[nf + (lane >> 2)][lane & 3];   // rows nf .. nf + 3 = the last four frames
+      __syncwarp(0xffffu);
+      w.dm[lane >> 2][lane & 3] = v;
+    }
     if (lane == 0) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) w.src[0][q] = w.src[nf][q];
@@ -446,7 +504,10 @@ extern "C" int m3d_viterbi_filter(const double* cand_dev, int64_t S, int64_t F, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned short* codes = nullptr;
   const size_t bytes = sizeof(unsigned short) * (size_t)S * F * n_back * P;
-  cudaError_t e = cudaMallocAsync(&codes, bytes, st);
+  int cur_dev = device;
+  cudaGetDevice(&cur_dev);
+  cudaMemPool_t pool = m3d_scratch_pool(cur_dev);
+  cudaError_t e = pool ? cudaMallocFromPoolAsync(&codes, bytes, pool, st) : cudaMallocAsync(&codes, bytes, st);
   if (e != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
   const unsigned blocks = (unsigned)((S + VT_WARPS - 1) / VT_WARPS);
   static const bool force_general = getenv("M3D_VITERBI_GENERAL") != nullptr;  // developer A/B switch
