@@ -520,5 +520,6 @@ extern "C" int m3d_viterbi_filter(const double* cand_dev, int64_t S, int64_t F, 
                                                 dup_thres * dup_thres, log_missing, codes, out_dev, choice_dev);
   const int rc = m3d_check_launch("k_viterbi");
   cudaFreeAsync(codes, st);
+  if (pool && bytes > (size_t(1) << 30)) cudaMemPoolTrimTo(pool, size_t(1) << 30);  // keep at most 1 GiB cached
   return rc;
 }
