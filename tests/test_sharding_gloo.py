@@ -38,7 +38,7 @@ class OracleGroup:
         return og.triangulate_ransac(self.cameras, pts, min_cams=min_cams)
 
 
-def _worker(rank, world, port, n_frames, ransac, tmp):
+def _worker(rank, world, port, n_frames, ransac, tmp, tile="auto"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,7 +47,7 @@ def _worker(rank, world, port, n_frames, ransac, tmp):
         cg = OracleGroup(dicts)
         X = synth.make_tracks(n_frames, 2, n_joints=5, seed=31).reshape(-1, 3)
         p2 = synth.corrupt(og.project(cg.cameras, X), seed=31, p_outlier=0.2 if ransac else 0.0, p_missing=0.1)
-        p3d, err = sharding.triangulate_sharded(cg, p2, n_frames, ransac=ransac)
+        p3d, err = sharding.triangulate_sharded(cg, p2, n_frames, ransac=ransac, tile_frames=tile)
         if rank == 0:
             np.savez(tmp, p3d=p3d, err=err, p2=p2)
         else:
@@ -56,10 +56,10 @@ def _worker(rank, world, port, n_frames, ransac, tmp):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,ransac", [(11, False), (6, True)])
-def test_sharded_matches_single_process(tmp_path, n_frames, ransac):
+@pytest.mark.parametrize("n_frames,ransac,tile", [(11, False, "auto"), (6, True, "auto"), (7, True, 2), (9, False, 1)])
+def test_sharded_matches_single_process(tmp_path, n_frames, ransac, tile):
     tmp = str(tmp_path / "out.npz")
-    mp.spawn(_worker, args=(2, _free_port(), n_frames, ransac, tmp), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_frames, ransac, tmp, tile), nprocs=2, join=True)
     r = np.load(tmp)
     cg = OracleGroup(synth.make_rig(4, "pinhole", seed=31))
     if ransac:
@@ -68,6 +68,15 @@ def test_sharded_matches_single_process(tmp_path, n_frames, ransac):
         p3d, err = cg.triangulate_with_error(r["p2"])
     assert np.array_equal(r["p3d"], p3d, equal_nan=True)     # uneven shards, global frame order
     assert np.array_equal(r["err"], err, equal_nan=True)
+
+
+def test_round_robin_tiles_partition():
+    for n in (0, 1, 7, 1000):
+        for w in (1, 2, 3, 8):
+            for t in (1, 3, 256):
+                fr = [sharding.tile_frames_of(n, r, w, t) for r in range(w)]
+                assert np.array_equal(np.sort(np.concatenate(fr)), np.arange(n))
+                assert all((f[1:] > f[:-1]).all() for f in fr if f.size > 1)
 
 
 def test_frame_ranges_partition():
