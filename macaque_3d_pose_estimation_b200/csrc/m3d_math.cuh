@@ -78,6 +78,19 @@ M3D_HD double rcp(double a) {
 #endif
 }
 
+// One Newton step on the hardware seed: relative error ~2^-40.  For quantities that only steer an
+// iteration (the Newton step of dlt_solve_warp), never for a value that is returned.
+M3D_HD double rcp_coarse(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / a;
+#endif
+}
+
 M3D_HD double sqrt_fast(double a) {
 #if defined(__CUDA_ARCH__)
   double y;
@@ -587,7 +600,8 @@ __device__ __forceinline__ void dlt_solve_warp(const Gram& G, bool active, doubl
     const double pp = p0 * p0 + p1 * p1 + p2 * p2;
     const double wl = G.w - lam;
     const double num = wl * det - q;
-    const double iden = rcp(det * det + pp);
+    // 2^-40 is plenty for the step: its error is second order in what is left of the iteration
+    const double iden = rcp_coarse(det * det + pp);
     dl = det * num * iden;
     crit = fabs(dl) <= tol * det;
     if (it >= 2 && !crit) {

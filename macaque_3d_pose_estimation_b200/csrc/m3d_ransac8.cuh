@@ -21,7 +21,8 @@
 
 namespace m3d {
 
-// shared memory of one warp: gc[8][10] | raw[8][2] | ghigh[10][8] | glow[10][32]   (local camera order)
+// shared memory of one warp: gc[8][10] | raw[8][2] | ghigh[8][10] | glow[5][32] double2   (local camera order;
+// the two tables hold a Gram as five 16-byte pairs (h0 h1)(h2 h3)(h4 h5)(g0 g1)(g2 w))
 constexpr int R8_RAW = 80, R8_GH = 96, R8_GL = 176, R8_WARP_DOUBLES = 176 + 320;
 constexpr int R8_ZEROS = 16;
 inline size_t ransac8_smem_bytes() {
@@ -46,8 +47,8 @@ k_ransac_search8(const RigDev* __restrict__ rig_g, const double* __restrict__ xy
   }
   __syncthreads();
   double* wrec = zeros + R8_ZEROS + warp * R8_WARP_DOUBLES;  // gc[8][10] | raw[8][2]
-  double* ghigh = wrec + R8_GH;                              // [10][8]  sums kept by the high bits
-  double* glow = wrec + R8_GL + lane;                        // [10][32] sums kept by the low bits (= lane)
+  double* ghigh = wrec + R8_GH;                              // [8][10]     sums kept by the high bits
+  double2* glow = reinterpret_cast<double2*>(wrec + R8_GL) + lane;  // [5][32] x 2 sums kept by the low bits (= lane)
   const double T1 = thr < init_best ? thr : init_best;
   const int lc = lane & 7, lq = lane >> 3;  // scoring: camera / candidate slot of this lane
 
@@ -134,15 +135,14 @@ k_ransac_search8(const RigDev* __restrict__ rig_g, const double* __restrict__ xy
         a2 += s[lq + 8];  // lq >= 2: reads past the block, never stored
         if (in && bit) dhigh |= 1u << ((lrank >> (4 * (klow + b))) & 15u);
       }
-      ghigh[lq * 8 + lc] = a0;
-      ghigh[(lq + 4) * 8 + lc] = a1;
-      if (lq < 2) ghigh[(lq + 8) * 8 + lc] = a2;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) glow[32 * i] = gl.h[i];
-      glow[32 * 6] = gl.g[0];
-      glow[32 * 7] = gl.g[1];
-      glow[32 * 8] = gl.g[2];
-      glow[32 * 9] = gl.w;
+      ghigh[lc * 10 + lq] = a0;
+      ghigh[lc * 10 + lq + 4] = a1;
+      if (lq < 2) ghigh[lc * 10 + lq + 8] = a2;
+      glow[0] = make_double2(gl.h[0], gl.h[1]);
+      glow[32] = make_double2(gl.h[2], gl.h[3]);
+      glow[64] = make_double2(gl.h[4], gl.h[5]);
+      glow[96] = make_double2(gl.g[0], gl.g[1]);
+      glow[128] = make_double2(gl.g[2], gl.w);
       __syncwarp();
     }
 
@@ -165,13 +165,19 @@ k_ransac_search8(const RigDev* __restrict__ rig_g, const double* __restrict__ xy
       double X, Y, Z;
       {
         Gram G;
-        const double* t = ghigh + hi;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) G.h[i] = glow[32 * i] + t[i * 8];
-        G.g[0] = glow[32 * 6] + t[6 * 8];
-        G.g[1] = glow[32 * 7] + t[7 * 8];
-        G.g[2] = glow[32 * 8] + t[8 * 8];
-        G.w = glow[32 * 9] + t[9 * 8];
+        const double2* t = reinterpret_cast<const double2*>(ghigh + 10 * hi);
+        const double2 l0 = glow[0], l1 = glow[32], l2 = glow[64], l3 = glow[96], l4 = glow[128];
+        const double2 h0 = t[0], h1 = t[1], h2 = t[2], h3 = t[3], h4 = t[4];
+        G.h[0] = l0.x + h0.x;
+        G.h[1] = l0.y + h0.y;
+        G.h[2] = l1.x + h1.x;
+        G.h[3] = l1.y + h1.y;
+        G.h[4] = l2.x + h2.x;
+        G.h[5] = l2.y + h2.y;
+        G.g[0] = l3.x + h3.x;
+        G.g[1] = l3.y + h3.y;
+        G.g[2] = l4.x + h4.x;
+        G.w = l4.y + h4.y;
         dlt_solve_warp(G, alive, X, Y, Z);
         alive = alive && (X == X);
       }
