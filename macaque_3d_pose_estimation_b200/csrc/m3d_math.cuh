@@ -582,7 +582,7 @@ __device__ __forceinline__ void dlt_solve_warp(const Gram& G, bool active, doubl
   double lam = 0.0;
   bool done = !active;
   const double tr = G.h[0] + G.h[3] + G.h[5];
-  const double tol = 1e-7 * rcp(tr * tr);  // lam_min(H - lam I) >= det / tr^2
+  const double tol = 1e-7 * rcp_coarse(tr * tr);  // lam_min(H - lam I) >= det / tr^2
   double c00, c01, c02, c11, c12, c22, det, p0, p1, p2, dl;
   bool pd, crit;
   const double b = G.h[1], c = G.h[2], e = G.h[4];

@@ -1,10 +1,11 @@
 // m3d_ransac16.cuh — subset search of K4 for rigs of 9..16 cameras: k_ransac_search8
 // (m3d_ransac8.cuh) with one more table level.  One warp = one point, lane = subset; a step
 // evaluates s = 32 * hi + lane with hi = 32 * top + mid:
-//   glow[10][32]  Gram sum of the cameras kept by bits 0..4   (index = lane)
-//   gmid[10][32]  ... by bits 5..9                            (index = mid)
-//   gtop[10][64]  ... by bits 10..15                          (index = top)
-// so a subset Gram is 30 shared loads + 20 adds.  The rank masks of the dropped cameras
+//   glow[5][32] x2  Gram sum of the cameras kept by bits 0..4   (index = lane)
+//   gmid[32][10]    ... by bits 5..9                            (index = mid)
+//   gtop[64][10]    ... by bits 10..15                          (index = top)
+// (a Gram = five 16-byte pairs (h0 h1)(h2 h3)(h4 h5)(g0 g1)(g2 w)), so a subset Gram is 15
+// 16-byte shared loads + 20 adds.  The rank masks of the dropped cameras
 // (suspicion order) are split the same way (dlow in a register, dmid by shuffle, dtop in shared
 // memory).  The local camera numbering (local index b = the bit of s that drops the camera) is
 // derived here from the slot's valid mask and physical suspicion order: with up to 65,519 subsets
@@ -15,8 +16,8 @@
 
 namespace m3d {
 
-// shared memory of one warp (doubles): gc[16][10] | raw[16][2] | glow[10][32] | gmid[10][32] |
-// gtop[10][64] | dtop[64] (as uint32, 32 doubles)
+// shared memory of one warp (doubles): gc[16][10] | raw[16][2] | glow[5][32]x2 | gmid[32][10] |
+// gtop[64][10] | dtop[64] (as uint32, 32 doubles)
 constexpr int R16_RAW = 160, R16_GL = 192, R16_GM = 512, R16_GT = 832, R16_DT = 1472,
               R16_WARP_DOUBLES = 1472 + 32;
 inline size_t ransac16_smem_bytes() {
@@ -38,13 +39,13 @@ __device__ __forceinline__ void gram_acc10(Gram& g, const double* s) {
   g.w += t4.y;
 }
 
-__device__ __forceinline__ void gram_store_col(double* t, int stride, const Gram& g) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) t[stride * i] = g.h[i];
-  t[stride * 6] = g.g[0];
-  t[stride * 7] = g.g[1];
-  t[stride * 8] = g.g[2];
-  t[stride * 9] = g.w;
+// a Gram as five 16-byte pairs, `stride` pairs apart
+__device__ __forceinline__ void gram_store_pairs(double2* t, int stride, const Gram& g) {
+  t[0] = make_double2(g.h[0], g.h[1]);
+  t[stride] = make_double2(g.h[2], g.h[3]);
+  t[2 * stride] = make_double2(g.h[4], g.h[5]);
+  t[3 * stride] = make_double2(g.g[0], g.g[1]);
+  t[4 * stride] = make_double2(g.g[2], g.w);
 }
 
 template <bool FULL, bool PO, int MINB>
@@ -66,9 +67,9 @@ k_ransac_search16(const RigDev* __restrict__ rig_g, const double* __restrict__ x
   __syncthreads();
   const int C = srig.n_cams;
   double* wrec = zeros + R8_ZEROS + warp * R16_WARP_DOUBLES;  // gc[16][10] | raw[16][2]
-  double* glow = wrec + R16_GL + lane;
-  double* gmid = wrec + R16_GM;
-  double* gtop = wrec + R16_GT;
+  double2* glow = reinterpret_cast<double2*>(wrec + R16_GL) + lane;  // [5][32] pairs
+  double2* gmid = reinterpret_cast<double2*>(wrec + R16_GM);         // [32][5] pairs
+  double2* gtop = reinterpret_cast<double2*>(wrec + R16_GT);         // [64][5] pairs
   uint32_t* dtop = reinterpret_cast<uint32_t*>(wrec + R16_DT);
   const double T1 = thr < init_best ? thr : init_best;
   const int lc = lane & 15, lq = lane >> 4;  // scoring: camera / candidate slot of this lane
@@ -170,10 +171,10 @@ k_ransac_search16(const RigDev* __restrict__ rig_g, const double* __restrict__ x
         if (bit0) dt0 |= rm;
         if (bit1) dt1 |= rm;
       }
-      gram_store_col(glow, 32, gl);
-      gram_store_col(gmid + lane, 32, gm);
-      gram_store_col(gtop + lane, 64, gt0);
-      gram_store_col(gtop + lane + 32, 64, gt1);
+      gram_store_pairs(glow, 32, gl);
+      gram_store_pairs(gmid + 5 * lane, 1, gm);
+      gram_store_pairs(gtop + 5 * lane, 1, gt0);
+      gram_store_pairs(gtop + 5 * (lane + 32), 1, gt1);
       dtop[lane] = dt0;
       dtop[lane + 32] = dt1;
       __syncwarp();
@@ -198,14 +199,21 @@ k_ransac_search16(const RigDev* __restrict__ rig_g, const double* __restrict__ x
       double X, Y, Z;
       {
         Gram G;
-        const double* tm = gmid + mid;
-        const double* tt = gtop + top;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) G.h[i] = (glow[32 * i] + tm[32 * i]) + tt[64 * i];
-        G.g[0] = (glow[32 * 6] + tm[32 * 6]) + tt[64 * 6];
-        G.g[1] = (glow[32 * 7] + tm[32 * 7]) + tt[64 * 7];
-        G.g[2] = (glow[32 * 8] + tm[32 * 8]) + tt[64 * 8];
-        G.w = (glow[32 * 9] + tm[32 * 9]) + tt[64 * 9];
+        const double2* tm = gmid + 5 * mid;
+        const double2* tt = gtop + 5 * top;
+        const double2 l0 = glow[0], l1 = glow[32], l2 = glow[64], l3 = glow[96], l4 = glow[128];
+        const double2 m0 = tm[0], m1 = tm[1], m2 = tm[2], m3 = tm[3], m4 = tm[4];
+        const double2 t0 = tt[0], t1 = tt[1], t2 = tt[2], t3 = tt[3], t4 = tt[4];
+        G.h[0] = (l0.x + m0.x) + t0.x;
+        G.h[1] = (l0.y + m0.y) + t0.y;
+        G.h[2] = (l1.x + m1.x) + t1.x;
+        G.h[3] = (l1.y + m1.y) + t1.y;
+        G.h[4] = (l2.x + m2.x) + t2.x;
+        G.h[5] = (l2.y + m2.y) + t2.y;
+        G.g[0] = (l3.x + m3.x) + t3.x;
+        G.g[1] = (l3.y + m3.y) + t3.y;
+        G.g[2] = (l4.x + m4.x) + t4.x;
+        G.w = (l4.y + m4.y) + t4.y;
         dlt_solve_warp(G, alive, X, Y, Z);
         alive = alive && (X == X);
       }
