@@ -360,6 +360,14 @@ def run_gpu(args):
     tf = ctypes_double()
     if rank == 0 and lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
         roofline["fp64_peak_tflops_measured"] = tf.value
+        try:   # the binding bound: fp64 pipe slots (one per fp64 instruction and lane) from the committed ncu capture
+            per = float(tj["fp64_thread_instr_per_instance"])
+            ach = per * N / (ms_per_step * 1e-3) / 1e12
+            roofline["fp64"] = {"thread_instr_per_instance": per, "achieved": ach, "peak": tf.value / 2.0,
+                                "unit": "T fp64 instr/s (per GPU)", "frac": ach / (tf.value / 2.0),
+                                "source": tj.get("fp64_source")}
+        except Exception:
+            pass
     extra = {"mean_valid_views": float((~torch.isnan(xy[:, :, 0])).double().mean().item() * C)}
     if args.workload == "ransac":
         extra["mean_subsets_per_point"] = float(nev.double().mean().item())
