@@ -382,6 +382,7 @@ def run_gpu(args):
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
+        numa = bind_to_gpu_numa_node(local)     # host buffers on the memory next to this rank's GPU
         h_xy = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True)
         h_xy.copy_(xy[:, :n_e2e])
         h_p3d = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
@@ -417,7 +418,8 @@ def run_gpu(args):
         e2e = {"value": world * n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 16,
                "d2h_bytes_per_step": d2h, "joint_instances_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
                "api": "m3d_triangulate_%s_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"
-                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": world}
+                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": world,
+               "host_numa_node": numa}
         del h_xy, h_p3d, h_err
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:200]}
@@ -528,6 +530,29 @@ def ctypes_double():
 def ctypes_byref(x):
     import ctypes
     return ctypes.byref(x)
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
+    buffers allocated afterwards are local to that GPU's PCIe root (with 8 ranks the H2D streams
+    otherwise cross the socket interconnect).  Returns the node or None; never fails."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def main():
