@@ -1,15 +1,17 @@
 // m3d_ransac8.cuh — subset search of K4 for rigs of at most 8 cameras (the lab rig and every
-// BASELINE 8-view configuration).  Same three-kernel structure and the same decisions as
-// k_ransac_search (m3d_ransac.cuh, kept for larger rigs); what changes is the bookkeeping
-// around the solves, which was 60 % of the instructions there:
+// BASELINE 8-view configuration; m3d_ransac16.cuh adds one table level for 9..16 cameras).
+// Middle kernel of the three-kernel search described in m3d_ransac.cuh.  Its 16-lane-group
+// predecessor (tools/experiments/) spent 60 % of its instructions on bookkeeping around the
+// solves; here:
 //   * one WARP = one point, lane = subset: a step evaluates s = 32 * hi + lane.  All control
 //     flow of the search is warp-uniform.
 //   * cameras are renumbered per point by the bit of the enumeration step s that drops them
 //     (local index b; k_ransac_full writes the nibble lists), so the camera set of step s is
 //     simply ~s — no per-step mask loops.
-//   * the Gram sum of the cameras kept by the low five bits (the lane) stays in registers for
-//     the whole point; the (at most 8) sums for the high bits sit in a shared-memory table
-//     built once per point: a subset Gram is 10 broadcast loads + 10 adds.
+//   * two shared-memory tables built once per point hold the Gram sums of the cameras kept by
+//     the low five bits (indexed by the lane, conflict-free) and by the high bits (at most 8
+//     entries, broadcast): a subset Gram is ten 16-byte loads + 10 adds.  (Keeping the low sum in
+//     registers instead costs 20 registers and a quarter of the resident warps.)
 //   * the rank mask (suspicion order) of the dropped cameras is split the same way, so the
 //     most suspicious member of a subset is one shuffle and one find-first-set.
 //   * the Newton iteration of the DLT solve runs warp-convergent (every lane iterates until the
