@@ -75,6 +75,17 @@ int32_t m3d_rig_device(const m3d_rig* rig);
  * (cameras.py:252, utils.py:9-15). */
 int m3d_rig_extrinsics(const m3d_rig* rig, double* M_host);
 
+/* Subset-search strategy of m3d_triangulate_ransac on this rig.  The pruned search
+ * (pair certificates) gives the same selection as the exhaustive one by
+ * construction; the switch exists so that tests can check exactly that.
+ *   M3D_RANSAC_AUTO        pruned search when every camera of the rig is certified, else exhaustive
+ *   M3D_RANSAC_EXHAUSTIVE  always solve every subset in front of the selected one */
+enum { M3D_RANSAC_AUTO = 0, M3D_RANSAC_EXHAUSTIVE = 1 };
+int m3d_rig_set_ransac_mode(m3d_rig* rig, int32_t mode);
+/* Bit c set: camera c's distortion model is certified for the pruned search (plain pinhole
+ * k1 k2 p1 p2 k3 whose distortion map is strongly monotone on the whole plane). */
+int32_t m3d_rig_certified_mask(const m3d_rig* rig);
+
 /* ---- per-camera maps ------------------------------------------------------------- */
 /* Camera.undistort_points / FisheyeCamera.~ / OmnidirCamera.~ (cameras.py:310,376,498):
  * xy_dev (n,2) pixels of camera `cam` -> out_dev (n,2) normalised coordinates. */

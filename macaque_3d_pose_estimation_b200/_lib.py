@@ -47,6 +47,8 @@ SIGNATURES = {
     "m3d_rig_num_cams": (_I, [_P]),
     "m3d_rig_device": (_I, [_P]),
     "m3d_rig_extrinsics": (ctypes.c_int, [_P, _P]),
+    "m3d_rig_set_ransac_mode": (ctypes.c_int, [_P, _I]),
+    "m3d_rig_certified_mask": (_I, [_P]),
     "m3d_undistort_cam": (ctypes.c_int, [_P, _I, _P, _L, _P, _P]),
     "m3d_project_cam": (ctypes.c_int, [_P, _I, _P, _L, _P, _P]),
     "m3d_distort_cam": (ctypes.c_int, [_P, _I, _P, _L, _P, _P]),

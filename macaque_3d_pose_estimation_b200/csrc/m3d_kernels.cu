@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/m3d.h"
+#include "m3d_handle.h"
 #include "m3d_internal.h"
 #include "m3d_math.cuh"
 #include "m3d_point.cuh"
@@ -62,37 +63,6 @@ cudaMemPool_t m3d_scratch_pool(int device) {
   return pools[device];
 }
 
-#define M3D_CUDA(expr)                                                                    \
-  do {                                                                                    \
-    cudaError_t e__ = (expr);                                                             \
-    if (e__ != cudaSuccess)                                                               \
-      return fail(M3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
-  } while (0)
-
-struct m3d_rig {
-  RigDev dev;
-  RigDev* dev_g = nullptr;  // device-resident copy (kernels that index cameras per lane)
-  int device;
-  // stream-ordered scratch of the RANSAC launches comes from a private pool that keeps its
-  // memory between launches (the default pool trims at every synchronisation)
-  cudaMemPool_t pool = nullptr;
-  std::mutex pool_mutex;
-  // workspace of the *_host pipelines (lazily allocated, guarded by ws_mutex)
-  std::mutex ws_mutex;
-  static const int kSlots = 3;
-  int64_t ws_chunk = 0;
-  int ws_cams = 0;
-  double* ws_xy[kSlots] = {nullptr, nullptr, nullptr};
-  double* ws_p3d[kSlots] = {nullptr, nullptr, nullptr};
-  double* ws_err[kSlots] = {nullptr, nullptr, nullptr};
-  double* ws_xyp[kSlots] = {nullptr, nullptr, nullptr};
-  uint8_t* ws_picked[kSlots] = {nullptr, nullptr, nullptr};
-  int32_t* ws_subset[kSlots] = {nullptr, nullptr, nullptr};
-  int32_t* ws_neval[kSlots] = {nullptr, nullptr, nullptr};
-  cudaStream_t ws_stream[kSlots] = {nullptr, nullptr, nullptr};
-  bool ws_ransac = false;
-};
-
 typedef M3dDeviceGuard DeviceGuard;
 
 const RigDev* m3d_rig_dev(const m3d_rig* rig) { return &rig->dev; }
@@ -100,15 +70,6 @@ const RigDev* m3d_rig_dev(const m3d_rig* rig) { return &rig->dev; }
 // ---------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 ld_xy(const double* __restrict__ xy, int64_t idx) {
-  // 16-byte read-only load of one (x, y) observation
-  return __ldg(reinterpret_cast<const double2*>(xy) + idx);
-}
-
-__device__ __forceinline__ void st_xy(double* out, int64_t idx, double x, double y) {
-  reinterpret_cast<double2*>(out)[idx] = make_double2(x, y);
-}
-
 // ---------------------------------------------------------------------------------------
 // K1: undistort (C,N,2) -> (C,N,2); blockIdx.y selects the camera
 // ---------------------------------------------------------------------------------------
@@ -304,14 +265,6 @@ k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: camera-subset RANSAC — see m3d_ransac.cuh
-// ---------------------------------------------------------------------------------------
-#include "m3d_ransac.cuh"
-#include "m3d_ransac8.cuh"
-#include "m3d_ransac16.cuh"
-#include "m3d_possible.cuh"
-
-// ---------------------------------------------------------------------------------------
 // fp64 FMA peak probe (the second roofline of this path)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters) {
@@ -334,16 +287,9 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters) {
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-static int grid_for(int64_t N, int threads, int sm_count) {
-  // grid-stride kernels: enough blocks to cover N, capped at 32 waves of resident blocks
-  int64_t blocks = (N + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count * 8 * 32;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
-}
+static int grid_for(int64_t N, int threads, int sm_count) { return m3d_grid_for(N, threads, sm_count); }
 
-static int sm_count_of(int device) {
+int m3d_sm_count(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) return cached[device];
   int v = 148;
@@ -352,17 +298,6 @@ static int sm_count_of(int device) {
   return v;
 }
 
-#define M3D_DISPATCH_MODEL(rig, CALL)                                      \
-  do {                                                                     \
-    const bool full__ = ((rig)->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM)) != 0; \
-    const bool po__ = ((rig)->dev.flags & RIG_HAS_NONPINHOLE) == 0;        \
-    if (full__) {                                                          \
-      if (po__) { CALL(true, true); } else { CALL(true, false); }          \
-    } else {                                                               \
-      if (po__) { CALL(false, true); } else { CALL(false, false); }        \
-    }                                                                      \
-  } while (0)
-
 int m3d_check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
@@ -370,6 +305,7 @@ int m3d_check_launch(const char* what) {
   return M3D_OK;
 }
 static int check_launch(const char* what) { return m3d_check_launch(what); }
+static int sm_count_of(int device) { return m3d_sm_count(device); }
 
 // ---------------------------------------------------------------------------------------
 // C ABI
@@ -409,12 +345,19 @@ int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig*
     DeviceGuard g(device);
     cudaError_t e = cudaMalloc(&rig->dev_g, sizeof(RigDev));
     if (e == cudaSuccess) e = cudaMemcpy(rig->dev_g, &rig->dev, sizeof(RigDev), cudaMemcpyHostToDevice);
+    static const CumBinom cumb_host = make_cumbinom();
+    if (e == cudaSuccess) e = cudaMalloc(&rig->cumb_g, sizeof(CumBinom));
+    if (e == cudaSuccess) e = cudaMemcpy(rig->cumb_g, &cumb_host, sizeof(CumBinom), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       cudaFree(rig->dev_g);
+      cudaFree(rig->cumb_g);
       delete rig;
       return fail(M3D_ERR_CUDA, std::string("m3d_rig_create: ") + cudaGetErrorString(e));
     }
   }
+  build_cert(rig->dev, &rig->cert);
+  rig->cert_all = n_cams >= 2 && rig->cert.ok_mask == (1 << n_cams) - 1 &&
+                  (rig->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM)) == 0;
   *out = rig;
   return M3D_OK;
 }
@@ -443,10 +386,21 @@ void m3d_rig_destroy(m3d_rig* rig) {
     DeviceGuard g(rig->device);
     free_workspace(rig);
     cudaFree(rig->dev_g);
+    cudaFree(rig->cumb_g);
     if (rig->pool) cudaMemPoolDestroy(rig->pool);
   }
   delete rig;
 }
+
+int m3d_rig_set_ransac_mode(m3d_rig* rig, int32_t mode) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_rig_set_ransac_mode: rig is NULL");
+  if (mode != M3D_RANSAC_AUTO && mode != M3D_RANSAC_EXHAUSTIVE)
+    return fail(M3D_ERR_INVALID, "m3d_rig_set_ransac_mode: unknown mode");
+  rig->ransac_mode = mode;
+  return M3D_OK;
+}
+
+int32_t m3d_rig_certified_mask(const m3d_rig* rig) { return rig ? rig->cert.ok_mask : 0; }
 
 int32_t m3d_rig_num_cams(const m3d_rig* rig) { return rig ? rig->dev.n_cams : -1; }
 int32_t m3d_rig_device(const m3d_rig* rig) { return rig ? rig->device : -1; }
@@ -600,153 +554,6 @@ int m3d_reproj_error(const m3d_rig* rig, const double* p3d, const double* xy, in
   return check_launch("k_reproj");
 }
 
-// joint-instances per internal ransac launch: bounds the scratch (undistorted views + slots,
-// 16 C + 64 bytes per instance) to ~0.8 GB at C = 8
-static const int64_t kRansacChunk = 1 << 22;
-
-static int launch_ransac(const m3d_rig* rig, const double* xy, int64_t N, int undistort, int min_cams,
-                         double threshold, double init_best, double* p3d, uint8_t* picked,
-                         double* xy_picked, double* err, int32_t* subset, int32_t* neval,
-                         cudaStream_t st) {
-  const int C = rig->dev.n_cams;
-  const int sms = sm_count_of(rig->device);
-  const int64_t chunk = N < kRansacChunk ? N : kRansacChunk;
-  const bool small_rig = C <= 8;  // table-driven search on per-point records (m3d_ransac8.cuh)
-  double* U = nullptr;
-  RansacSlot* slots = nullptr;
-  unsigned long long* counter = nullptr;
-  {
-    m3d_rig* mrig = const_cast<m3d_rig*>(rig);
-    std::lock_guard<std::mutex> lock(mrig->pool_mutex);
-    if (!mrig->pool) {
-      cudaMemPoolProps props = {};
-      props.allocType = cudaMemAllocationTypePinned;
-      props.location.type = cudaMemLocationTypeDevice;
-      props.location.id = rig->device;
-      M3D_CUDA(cudaMemPoolCreate(&mrig->pool, &props));
-      unsigned long long keep = ~0ull;
-      M3D_CUDA(cudaMemPoolSetAttribute(mrig->pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-  }
-  M3D_CUDA(cudaMallocFromPoolAsync(&U, sizeof(double) * 2 * (size_t)(C > 0 ? C : 1) * chunk, rig->pool, st));
-  M3D_CUDA(cudaMallocFromPoolAsync(&slots, sizeof(RansacSlot) * (size_t)chunk, rig->pool, st));
-  M3D_CUDA(cudaMallocFromPoolAsync(&counter, sizeof(unsigned long long), rig->pool, st));
-  int rc = M3D_OK;
-  for (int64_t n0 = 0; n0 < N && rc == M3D_OK; n0 += chunk) {
-    const int64_t n = (N - n0) < chunk ? (N - n0) : chunk;
-    const int gridA = grid_for(n, 256, sms);
-#define CALLA(F, P, NC) \
-  k_ransac_full<F, P, NC><<<gridA, 256, 0, st>>>(rig->dev, xy, N, n0, n, undistort, min_cams, threshold, init_best, U, slots)
-#define CALL(F, P)                   \
-  do {                               \
-    if (C == 8) CALLA(F, P, 8);      \
-    else CALLA(F, P, 0);             \
-  } while (0)
-    M3D_DISPATCH_MODEL(rig, CALL);
-#undef CALL
-#undef CALLA
-    rc = check_launch("k_ransac_full");
-    if (rc) break;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) {
-      rc = fail(M3D_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
-      break;
-    }
-#define CALLC(F, P, MB)                                                                                   \
-  do {                                                                                                    \
-    auto kfn = k_ransac_search8<F, P, MB>;                                                                \
-    const size_t smem8 = ransac8_smem_bytes();                                                            \
-    int per_sm = 0;                                                                                       \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RANSAC_THREADS, smem8);                   \
-    if (per_sm < 1) per_sm = 1;                                                                           \
-    int64_t blocks = (int64_t)sms * per_sm;                                                               \
-    const int64_t need = (n + 32 * RANSAC_WARPS - 1) / (32 * RANSAC_WARPS);                               \
-    if (blocks > need) blocks = need;                                                                     \
-    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem8, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,   \
-                                                         init_best, U, slots, counter);                   \
-  } while (0)
-#define CALLD(F, P, MB)                                                                                   \
-  do {                                                                                                    \
-    auto kfn = k_ransac_search16<F, P, MB>;                                                               \
-    const size_t smem16 = ransac16_smem_bytes();                                                          \
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);                  \
-    int per_sm = 0;                                                                                       \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RANSAC_THREADS, smem16);                  \
-    if (per_sm < 1) per_sm = 1;                                                                           \
-    int64_t blocks = (int64_t)sms * per_sm;                                                               \
-    const int64_t need = (n + 32 * RANSAC_WARPS - 1) / (32 * RANSAC_WARPS);                               \
-    if (blocks > need) blocks = need;                                                                     \
-    kfn<<<(unsigned)blocks, RANSAC_THREADS, smem16, st>>>(rig->dev_g, xy, N, n0, n, min_cams, threshold,  \
-                                                          init_best, U, slots, counter);                  \
-  } while (0)
-    // rigs of at most 8 cameras: k_ransac_search8; 9..16 cameras: k_ransac_search16 (one more table
-    // level; 16 warps / SM at 128 registers, 52 KB shared memory per CTA).
-    // measured on B200 (cfg 3): 16 / 20 / 24 / 32 warps per SM (128 / 96 / 80 / 64 registers) run at
-    // 4.27 / 4.2 / 4.58 / 4.50e8 inst/s — 24 warps is the default, M3D_RANSAC_VARIANT=4|8 the others
-    static const int dev_variant = [] { const char* e = getenv("M3D_RANSAC_VARIANT"); return e ? atoi(e) : 0; }();
-#define CALL(F, P)                                   \
-  do {                                               \
-    if (!small_rig && dev_variant == 3) CALLD(F, P, 3); \
-    else if (!small_rig) CALLD(F, P, 4);             \
-    else if (dev_variant == 4) CALLC(F, P, 4);       \
-    else if (dev_variant == 8) CALLC(F, P, 8);       \
-    else CALLC(F, P, 6);                             \
-  } while (0)
-    M3D_DISPATCH_MODEL(rig, CALL);
-#undef CALL
-#undef CALLC
-#undef CALLD
-    rc = check_launch("k_ransac_search");
-    if (rc) break;
-    k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
-                                                         subset, neval);
-    rc = check_launch("k_ransac_emit");
-  }
-  cudaFreeAsync(U, st);
-  cudaFreeAsync(slots, st);
-  cudaFreeAsync(counter, st);
-  return rc;
-}
-
-int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
-                           int32_t min_cams, double threshold, double init_best, double* p3d,
-                           uint8_t* picked, double* xy_picked, double* err, int32_t* subset,
-                           int32_t* neval, void* stream) {
-  M3D_CHECK_RIG("m3d_triangulate_ransac");
-  if (N == 0) return M3D_OK;
-  if (!p3d || !err || (!xy && rig->dev.n_cams > 0))
-    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac: NULL buffer");
-  return launch_ransac(rig, xy, N, undistort, min_cams, threshold, init_best, p3d, picked, xy_picked,
-                       err, subset, neval, st);
-}
-
-int m3d_triangulate_possible(const m3d_rig* rig, const double* xy, int64_t N, int32_t P, int32_t undistort,
-                             int32_t min_cams, double threshold, double init_best, double* p3d,
-                             uint8_t* picked, double* xy_picked, double* err, int32_t* index,
-                             int32_t* neval, void* stream) {
-  M3D_CHECK_RIG("m3d_triangulate_possible");
-  const int C = rig->dev.n_cams;
-  if (P < 1 || C * P > POSS_SLOTS)
-    return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: cameras * candidates must be between 1 and 32");
-  if (N == 0) return M3D_OK;
-  if (!p3d || !err || (!xy && C > 0)) return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: NULL buffer");
-  const size_t smem = possible_smem_bytes();
-  int64_t blocks = (N + POSS_WARPS - 1) / POSS_WARPS;
-  const int64_t cap = (int64_t)sms * 8;
-  if (blocks > cap) blocks = cap;
-#define CALL(F, Pm)                                                                                   \
-  do {                                                                                                \
-    auto kfn = k_possible<F, Pm>;                                                                     \
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-    kfn<<<(unsigned)blocks, POSS_WARPS * 32, smem, st>>>(rig->dev_g, xy, N, P, undistort, min_cams,   \
-                                                         threshold, init_best, p3d, picked, xy_picked, \
-                                                         err, index, neval);                          \
-  } while (0)
-  M3D_DISPATCH_MODEL(rig, CALL);
-#undef CALL
-  return check_launch("k_possible");
-}
-
 int m3d_triangulate_ls(const m3d_rig* rig, const double* xy, const uint8_t* use, int64_t N,
                        double* p3d, void* stream) {
   M3D_CHECK_RIG("m3d_triangulate_ls");
@@ -809,7 +616,7 @@ static int host_pipeline(m3d_rig* rig, const double* xy, int64_t N, int undistor
                               err ? rig->ws_err[slot] : nullptr, st, sms);
       if (rc) return rc;
     } else {
-      rc = launch_ransac(rig, rig->ws_xy[slot], n, undistort, min_cams, threshold, init_best,
+      rc = m3d_launch_ransac(rig, rig->ws_xy[slot], n, undistort, min_cams, threshold, init_best,
                          rig->ws_p3d[slot], picked ? rig->ws_picked[slot] : nullptr,
                          xy_picked ? rig->ws_xyp[slot] : nullptr, rig->ws_err[slot],
                          subset ? rig->ws_subset[slot] : nullptr, neval ? rig->ws_neval[slot] : nullptr, st);

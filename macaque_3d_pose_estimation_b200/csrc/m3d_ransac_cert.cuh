@@ -1,0 +1,542 @@
+// m3d_ransac_cert.cuh — K4c: camera-subset RANSAC (CameraGroup.triangulate_possible with one
+// candidate per camera, cameras.py:639-743) with EXACT PRE-SOLVE PRUNING by pair certificates.
+//
+// The reference visits the subsets of the k valid cameras in itertools.product order and stops at
+// the first one whose mean reprojection error is < T1 = min(threshold, init_best).  Almost all of
+// the subsets in front of that one contain a grossly wrong detection; the exhaustive kernels
+// (m3d_ransac8.cuh / m3d_ransac16.cuh) reject each of them with a DLT solve and a projection.  Here
+// a subset is rejected without any arithmetic when it contains a PAIR of cameras whose two
+// observations cannot both lie within the accepted residual budget of ANY 3D point (m3d_cert.h;
+// proof in DESIGN.md 3.2c).  The test is conservative: a subset it rejects has
+// mean error >= T1 for certain, a subset it cannot reject is solved and scored exactly as before,
+// so the selected subset, its error and the number of subsets the reference would have evaluated
+// are unchanged.
+//
+// One THREAD = one point, one kernel, no scratch:
+//   * 8-camera rigs: raw and undistorted observations live in registers (camera loops unrolled,
+//     camera parameters and the 28 essential matrices are constant-bank operands); other rigs
+//     (2..16 cameras) run the same code with run-time loops;
+//   * cameras are numbered by the bit of the enumeration step that drops them in a fixed frame
+//     (bit C - 1 - c), so that "next subset" is one add on the dropped-camera mask
+//     d' = ((d | ~v) + 1) & v and ascending d is the reference's ascending step index s;
+//   * pruning is a JUMP: if the kept set contains a certified-bad pair whose lower bit is p, every
+//     step up to the next one that sets bit p keeps that pair, so the search continues at
+//     ((d >> p) | 1) << p.  The pair masks are computed once per point at the weakest radius
+//     rho = T1 (k - 1) (valid for every subset size after the full set);
+//   * subsets that survive are solved (dlt_solve) and scored against the raw pixels exactly like
+//     the full set; pass 2 (no subset under T1: strict arg-min over all admissible subsets) runs
+//     without pruning, because a pruned subset may still be the arg-min;
+//   * the number of subsets the reference would have triangulated follows combinatorially from the
+//     stopping step (cumulative binomials), no counting loop.
+#pragma once
+#include "m3d_cert.h"
+#include "m3d_math.cuh"
+#include "m3d_point.cuh"
+#if defined(__CUDACC__)
+#include "m3d_ransac.cuh"
+#endif
+
+namespace m3d {
+
+// #{ 1 <= s <= n : popc(s) <= m }  (n < 2^16); cumb = CumBinom::v flattened
+M3D_HD int count_adm(const uint32_t* cumb, uint32_t n, int m) {
+  if (m < 0) return 0;
+  int ones = 0, total = 0;
+  for (int i = 15; i >= 0; --i) {
+    if ((n >> i) & 1u) {
+      const int rem = m - ones;
+      if (rem < 0) break;
+      total += (int)cumb[i * 17 + (rem < i ? rem : i)];
+      ++ones;
+    }
+  }
+  if (ones <= m) total += 1;  // n itself (the loop was not cut short)
+  return total - 1;           // s = 0 is not counted here
+}
+
+struct XY {
+  double x, y;
+};
+
+struct CertOut {
+  double X, Y, Z, err;  // err: 0.0 when nothing was selected (cameras.py:675)
+  uint32_t sel;         // cameras of the selection, bit C - 1 - c
+  int32_t s_sel;        // step index of the selection, -1 when none
+  int32_t neval;        // subsets the reference would have triangulated
+  int32_t n_solved;     // subsets this search solved (diagnostic of the CPU test tier)
+  int32_t n_visited;    // steps of cert_advance (diagnostic)
+};
+
+// ---- building blocks (shared by the reference single-thread form below, the kernels and the CPU
+// test tier).  NC > 0: camera count known at compile time (loops unroll, arrays live in registers);
+// NC == 0: run-time count up to M3D_MAXC.  Bit position of camera c: C - 1 - c.
+
+// per-camera undistortion (cameras.py:608-614) and the two validity masks
+template <bool PO, int NC>
+M3D_HD void cert_undistort(const RigDev& rig, const XY* raw, int undistort, XY* xh, uint32_t& v, uint32_t& u) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const uint32_t TOP = (uint32_t)(C - 1);
+  v = 0, u = 0;
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    if (c < C) {
+      double x = raw[c].x, y = raw[c].y;
+      if (x == x) {  // valid: raw x not NaN (cameras.py:658-659)
+        v |= 1u << (TOP - c);
+        if (undistort) undistort_point<false, PO>(rig.cam[c], raw[c].x, raw[c].y, x, y);
+        if (x == x) u |= 1u << (TOP - c);  // usable inside triangulate (cameras.py:630)
+      }
+      xh[c].x = x;
+      xh[c].y = y;
+    }
+  }
+}
+
+// triangulate from the usable cameras of `kept`, score against the raw pixels of all of `kept`
+// (cameras.py:697-701): mean reprojection error, NaN when undefined
+template <bool PO, int NC>
+M3D_HD double cert_eval(const RigDev& rig, const XY* raw, const XY* xh, uint32_t kept, uint32_t uc, double& X,
+                        double& Y, double& Z) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const uint32_t TOP = (uint32_t)(C - 1);
+  X = Y = Z = qnan();
+  if (M3D_POPC(uc) < 2) return qnan();
+  Gram G;
+  gram_zero(G);
+#pragma unroll
+  for (int c = 0; c < CC; ++c)
+    if (c < C && ((uc >> (TOP - c)) & 1u)) gram_add_camera(G, rig.cam[c], xh[c].x, xh[c].y);
+  dlt_solve(G, X, Y, Z);
+  double sum = 0.0;
+  int m = 0;
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    if (c < C && ((kept >> (TOP - c)) & 1u)) {
+      double pu, pv;
+      project_point<false, PO>(rig.cam[c], X, Y, Z, pu, pv);
+      const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
+      if (e == e) {
+        sum += e;
+        ++m;
+      }
+    }
+  }
+  return (m >= 2) ? sum / (double)m : qnan();
+}
+
+// pair certificates at residual budget rho (m3d_cert.h): badrow[p] = certified-bad partners of bit
+// position p at HIGHER positions
+template <int NC>
+M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, const XY* xh, uint32_t u,
+                       double rho, uint32_t* badrow) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const uint32_t TOP = (uint32_t)(C - 1);
+  double dl[CC];
+  uint32_t pairable = 0;
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    dl[c] = 0.0;
+    badrow[c] = 0;
+    if (c < C && ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0) {
+      double pu, pv;
+      distort_pinhole<false>(rig.cam[c], xh[c].x, xh[c].y, pu, pv);
+      const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
+      if (e < 1e3) {  // finite centre, finite raw pixel
+        dl[c] = e;
+        pairable |= 1u << (TOP - c);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < CC; ++a) {
+#pragma unroll
+    for (int b = a + 1; b < CC; ++b) {
+      if (b >= C || ((pairable >> (TOP - a)) & (pairable >> (TOP - b)) & 1u) == 0) continue;
+      const double* E = cert.E[pair_index(a, b, C)];
+      const double ax = xh[a].x, ay = xh[a].y, qx = xh[b].x, qy = xh[b].y;
+      const double ea0 = E[0] * ax + E[1] * ay + E[2];
+      const double ea1 = E[3] * ax + E[4] * ay + E[5];
+      const double ea2 = E[6] * ax + E[7] * ay + E[8];
+      const double F = qx * ea0 + qy * ea1 + ea2;
+      const double tb0 = E[0] * qx + E[3] * qy + E[6];
+      const double tb1 = E[1] * qx + E[4] * qy + E[7];
+      const double A = (fabs(tb0) + fabs(tb1)) * cert.inv_mf[a];
+      const double B = (fabs(ea0) + fabs(ea1)) * cert.inv_mf[b];
+      const double D = rho + dl[a] + dl[b];
+      const double rhs = ((A > B ? A : B) + 0.25 * E[9] * D) * D;
+      if (fabs(F) > rhs * (1.0 + 1e-9)) badrow[TOP - b] |= 1u << (TOP - a);
+    }
+  }
+}
+
+// residual budget of the pair certificates: the weakest radius any subset after the full set can
+// have (|S| <= k - 1), plus 1e-6 px for the rounding of the reference's own projections
+M3D_HD double cert_rho(double T1, int k) { return T1 * (double)(k - 1) * (1.0 + 1e-9) + 1e-6; }
+
+M3D_HD uint32_t cert_next(uint32_t v, uint32_t d) { return ((d | ~v) + 1u) & v; }
+
+// Smallest dropped-camera mask >= d0 in enumeration order (0 = d0 wrapped around: exhausted) whose
+// kept set contains no certified-bad pair and at least min_cams cameras; 0 when there is none.
+// One pass from the top bit down: follow d0 until a camera it keeps conflicts with a camera kept
+// above it — that camera has to go, which makes the mask larger than d0 at the highest possible
+// position; from there on keep every camera that does not conflict (lexicographically smallest
+// completion).  Every mask in between keeps a conflicting pair, i.e. is certified-bad.
+template <int NC>
+M3D_HD uint32_t cert_advance(uint32_t v, uint32_t d0, const uint32_t* badrow, int min_cams) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  while (d0 != 0) {
+    uint32_t kept = 0, dn = 0;
+    bool departed = false;
+#pragma unroll
+    for (int p = CC - 1; p >= 0; --p) {
+      const uint32_t bit = 1u << p;
+      if (v & bit) {
+        const bool conflict = (badrow[p] & kept) != 0;
+        const bool follow = !departed && ((d0 & bit) != 0);
+        if (conflict && !follow) departed = true;
+        if (conflict || follow) dn |= bit;
+        else kept |= bit;
+      }
+    }
+    if (M3D_POPC(kept) >= min_cams) return dn;
+    d0 = cert_next(v, dn);
+  }
+  return 0;
+}
+
+// step index s of a dropped-camera mask: its bits at the valid positions, compacted
+template <int NC>
+M3D_HD uint32_t cert_step_index(uint32_t v, uint32_t d) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  uint32_t s = 0;
+  int j = 0;
+#pragma unroll
+  for (int p = 0; p < CC; ++p) {
+    if ((v >> p) & 1u) {
+      s |= ((d >> p) & 1u) << j;
+      ++j;
+    }
+  }
+  return s;
+}
+
+// One point of the pruned subset search, start to end in one thread: the reference form of the
+// algorithm (CPU test tier, tests/host_harness.cpp) — the kernels below run the same blocks, split
+// over two launches so that the lanes of a warp stay busy.
+template <bool PO, int NC>
+M3D_HD void ransac_cert_point(const RigDev& rig, const CertDev& cert, const uint32_t* cumb, const XY* raw,
+                              int undistort, int min_cams, double thr, double init_best, bool use_cert,
+                              CertOut& out) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const double T1 = thr < init_best ? thr : init_best;
+  XY xh[CC];
+  uint32_t v, u;
+  cert_undistort<PO, NC>(rig, raw, undistort, xh, v, u);
+  const int k = M3D_POPC(v);
+  uint32_t badrow[CC];
+#pragma unroll
+  for (int p = 0; p < CC; ++p) badrow[p] = 0;
+  uint32_t d = 0, best_d = 0;
+  int pass = 0;
+  bool have = false, ran_out = false;
+  double best_err = init_best, bx = qnan(), by = qnan(), bz = qnan();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  int n_solved = 0;
+  for (;;) {
+    const uint32_t kept = v & ~d;
+    double X, Y, Z;
+    const double err = cert_eval<PO, NC>(rig, raw, xh, kept, kept & u, X, Y, Z);
+    ++n_solved;
+    // ---- accept / continue (cameras.py:703-713)
+    bool stop = false;
+    if (pass == 0) {
+      if (err < best_err) {
+        best_err = err, best_d = 0, have = true, bx = X, by = Y, bz = Z;
+        stop = err < thr;
+      }
+      if (k < 2 || k <= min_cams) stop = true;  // every smaller subset would be skipped (:691)
+      if (!stop && use_cert) cert_pairs<NC>(rig, cert, raw, xh, u, cert_rho(T1, k), badrow);
+      pass = 1;
+    } else if (pass == 1) {
+      if (err < T1) {
+        best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
+        stop = true;
+      }
+    } else {
+      if (err < best_err) best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
+    }
+    if (stop) break;
+    d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
+    if (d == 0 && pass == 1 && T1 < best_err) {
+      // nothing under T1: rescan everything for the strict arg-min, without pruning (a pruned
+      // subset has err >= T1 but may still be the arg-min)
+      pass = 2;
+#pragma unroll
+      for (int p = 0; p < CC; ++p) badrow[p] = 0;
+      d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+    }
+    if (d == 0) {
+      ran_out = true;
+      break;
+    }
+  }
+  const uint32_t s_sel = cert_step_index<NC>(v, best_d);
+  out.X = bx;
+  out.Y = by;
+  out.Z = bz;
+  out.err = have ? best_err : 0.0;
+  out.s_sel = have ? (int32_t)s_sel : -1;
+  out.sel = have ? (v & ~best_d) : 0u;
+  int ne = 1;
+  if (ran_out) ne += count_adm(cumb, (1u << k) - 1u, k - min_cams);  // never stopped
+  else if (best_d != 0) ne += count_adm(cumb, s_sel, k - min_cams);  // stopped at s_sel in pass 1
+  out.neval = ne;
+  out.n_solved = n_solved * (pass == 2 ? -1 : 1);  // negative: the point needed the arg-min pass
+  out.n_visited = 0;
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------
+// kernels.  Per-point cost is 1 evaluation for ~20 % of the points, 2 for most, 10+ for a tail:
+// run start-to-end per thread, a warp waits for its slowest lane (measured: 13 evaluations per
+// warp for 2.4 per point).  Hence two launches:
+//   k_cert_setup   thread = point, convergent: undistort, full-set evaluation, decision, pair
+//                  certificates; writes the result slot of every point and, for the undecided
+//                  ones, a record (raw + undistorted views, pair masks) into a compact queue
+//   k_cert_search  persistent lanes: every lane owns one queued point and evaluates one
+//                  surviving subset per trip; a lane that finishes takes the next record at once,
+//                  so all 32 lanes evaluate on (almost) every trip
+//   k_ransac_emit  (m3d_ransac.cuh) expands the slots into the reference's outputs
+// Record q: fields of 16 bytes, field f of record q at ((q / 32) * F + f) * 32 + q % 32 (so that 32
+// consecutive records are read / written with full sectors):
+//   f <  C       raw (x, y) of camera f          f < 2C   undistorted (x, y) of camera f - C
+//   f == 2C      v | u << 16, point index, -, -  f == 2C + 1, 2C + 2   best_err, bx | by, bz
+//   f >= 2C + 3  pair masks, 16 bits per bit position
+// ---------------------------------------------------------------------------------------
+M3D_HD int cert_record_fields(int C) { return 2 * C + 3 + (C + 7) / 8; }
+
+template <bool PO, int NC>
+__global__ void __launch_bounds__(128, NC == 8 ? 3 : 2)
+k_cert_setup(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev cert,
+             const double* __restrict__ xy, int64_t ld, int64_t n0, int64_t n, int undistort, int min_cams,
+             double thr, double init_best, RansacSlot* __restrict__ slots, double2* __restrict__ rec,
+             unsigned int* __restrict__ n_rec) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const int F = cert_record_fields(C);
+  const double T1 = thr < init_best ? thr : init_best;
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together (the queue append is warp-aggregated)
+  const int64_t n_round = (n + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool inb = i < n;
+    XY raw[CC], xh[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      if (c < C) {
+        double2 q = make_double2(qnan(), qnan());
+        if (inb) q = ld_xy(xy, (int64_t)c * ld + n0 + i);
+        raw[c].x = q.x;
+        raw[c].y = q.y;
+      }
+    }
+    uint32_t v, u;
+    cert_undistort<PO, NC>(rig, raw, undistort, xh, v, u);
+    const int k = __popc(v);
+    double X, Y, Z;
+    const double err = cert_eval<PO, NC>(rig, raw, xh, v, u, X, Y, Z);
+    bool stop = false, have = false;
+    double best_err = init_best;
+    if (err < best_err) {
+      best_err = err, have = true;
+      stop = err < thr;
+    }
+    if (k < 2 || k <= min_cams) stop = true;  // every smaller subset would be skipped (:691)
+    if (inb) {
+      RansacSlot sl;
+      sl.best_err = best_err;
+      sl.bx = have ? X : qnan();
+      sl.by = have ? Y : qnan();
+      sl.bz = have ? Z : qnan();
+      sl.ord = 0;
+      sl.masks = __brev(v) >> (32 - C);  // physical camera numbering for k_ransac_emit
+      sl.vlist = 0;
+      sl.best_s = have ? 0 : -1;
+      sl.neval = 1;
+      sl.decided = stop ? 1 : 0;
+      sl.uml = 0;
+      slots[i] = sl;
+    }
+    const bool queue = inb && !stop;
+    const uint32_t qb = __ballot_sync(FULLM, queue);
+    if (qb) {
+      uint32_t badrow[CC];
+      if (queue) cert_pairs<NC>(rig, cert, raw, xh, u, cert_rho(T1, k), badrow);
+      unsigned int base = 0;
+      if (lane == __ffs(qb) - 1) base = atomicAdd(n_rec, (unsigned int)__popc(qb));
+      base = __shfl_sync(FULLM, base, __ffs(qb) - 1);
+      if (queue) {
+        const unsigned int q = base + (unsigned int)__popc(qb & ((1u << lane) - 1u));
+        double2* r = rec + ((size_t)(q >> 5) * F) * 32 + (q & 31u);
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          if (c < C) {
+            r[(size_t)c * 32] = make_double2(raw[c].x, raw[c].y);
+            r[(size_t)(C + c) * 32] = make_double2(xh[c].x, xh[c].y);
+          }
+        }
+        uint4 m0 = make_uint4(v | (u << 16), (uint32_t)i, 0u, 0u);
+        reinterpret_cast<uint4*>(r)[(size_t)(2 * C) * 32] = m0;
+        r[(size_t)(2 * C + 1) * 32] = make_double2(best_err, have ? X : qnan());
+        r[(size_t)(2 * C + 2) * 32] = make_double2(have ? Y : qnan(), have ? Z : qnan());
+#pragma unroll
+        for (int g = 0; g < (CC + 7) / 8; ++g) {
+          if (8 * g < C) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int p0 = 8 * g + 2 * j, p1 = p0 + 1;
+              w[j] = (p0 < CC ? (badrow[p0 < CC ? p0 : 0] & 0xffffu) : 0u) |
+                     ((p1 < CC ? (badrow[p1 < CC ? p1 : 0] & 0xffffu) : 0u) << 16);
+            }
+            reinterpret_cast<uint4*>(r)[(size_t)(2 * C + 3 + g) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool PO, int NC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ cumb, int min_cams, double thr,
+              double init_best, RansacSlot* __restrict__ slots, const double2* __restrict__ rec,
+              const unsigned int* __restrict__ n_rec, unsigned int* __restrict__ counter) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const int F = cert_record_fields(C);
+  const double T1 = thr < init_best ? thr : init_best;
+  const int lane = threadIdx.x & 31;
+  const unsigned int total = *n_rec;
+  XY raw[CC], xh[CC];
+  uint32_t badrow[CC];
+  uint32_t v = 0, u = 0, d = 0, best_d = 0, idx = 0;
+  int pass = 1;
+  bool active = false, drained = false, have = false;
+  double best_err = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+#pragma unroll 1
+  for (;;) {
+    // ---- lanes without a point take the next records of the queue
+    const bool need = !active && !drained;
+    const uint32_t nb = __ballot_sync(FULLM, need);
+    if (nb) {
+      unsigned int base = 0;
+      if (lane == __ffs(nb) - 1) base = atomicAdd(counter, (unsigned int)__popc(nb));
+      base = __shfl_sync(FULLM, base, __ffs(nb) - 1);
+      if (need) {
+        const unsigned int q = base + (unsigned int)__popc(nb & ((1u << lane) - 1u));
+        if (q < total) {
+          const double2* r = rec + ((size_t)(q >> 5) * F) * 32 + (q & 31u);
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            if (c < C) {
+              const double2 a = r[(size_t)c * 32], b = r[(size_t)(C + c) * 32];
+              raw[c].x = a.x, raw[c].y = a.y;
+              xh[c].x = b.x, xh[c].y = b.y;
+            }
+          }
+          const uint4 m0 = reinterpret_cast<const uint4*>(r)[(size_t)(2 * C) * 32];
+          v = m0.x & 0xffffu;
+          u = m0.x >> 16;
+          idx = m0.y;
+          const double2 b0 = r[(size_t)(2 * C + 1) * 32], b1 = r[(size_t)(2 * C + 2) * 32];
+          best_err = b0.x, bx = b0.y, by = b1.x, bz = b1.y;
+          have = bx == bx;  // the full set was accepted (its error is >= T1, else the point was decided)
+#pragma unroll
+          for (int g = 0; g < (CC + 7) / 8; ++g) {
+            if (8 * g < C) {
+              const uint4 w = reinterpret_cast<const uint4*>(r)[(size_t)(2 * C + 3 + g) * 32];
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (8 * g + 2 * j < CC) badrow[8 * g + 2 * j] = ww[j] & 0xffffu;
+                if (8 * g + 2 * j + 1 < CC) badrow[8 * g + 2 * j + 1] = ww[j] >> 16;
+              }
+            }
+          }
+          best_d = 0;
+          pass = 1;
+          active = true;
+          d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+          if (d == 0 && T1 < best_err) {  // every subset is certified-bad: arg-min scan
+            pass = 2;
+#pragma unroll
+            for (int p = 0; p < CC; ++p) badrow[p] = 0;
+            d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+          }
+        } else {
+          drained = true;
+        }
+      }
+    }
+    if (!__any_sync(FULLM, active)) break;
+    if (active) {
+      bool stop = false, ran_out = false;
+      if (d == 0) {
+        stop = ran_out = true;  // no candidate at all
+      } else {
+        const uint32_t kept = v & ~d;
+        double X, Y, Z;
+        const double err = cert_eval<PO, NC>(rig, raw, xh, kept, kept & u, X, Y, Z);
+        if (pass == 1) {
+          if (err < T1) {
+            best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
+            stop = true;
+          }
+        } else if (err < best_err) {
+          best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
+        }
+        if (!stop) {
+          d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
+          if (d == 0 && pass == 1 && T1 < best_err) {
+            pass = 2;
+#pragma unroll
+            for (int p = 0; p < CC; ++p) badrow[p] = 0;
+            d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+          }
+          if (d == 0) stop = ran_out = true;
+        }
+      }
+      if (stop) {
+        const int k = __popc(v);
+        const uint32_t s_sel = cert_step_index<NC>(v, best_d);
+        int ne = 1;
+        if (ran_out) ne += count_adm(cumb, (1u << k) - 1u, k - min_cams);
+        else ne += count_adm(cumb, s_sel, k - min_cams);
+        RansacSlot* sl = slots + idx;
+        sl->best_err = best_err;
+        sl->bx = bx;
+        sl->by = by;
+        sl->bz = bz;
+        sl->best_s = have ? (int32_t)s_sel : -1;
+        sl->neval = ne;
+        active = false;
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace m3d

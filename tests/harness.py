@@ -21,7 +21,7 @@ def _stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("m3d_math.cuh", "m3d_point.cuh", "m3d_rig.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("m3d_math.cuh", "m3d_point.cuh", "m3d_rig.h", "m3d_cert.h", "m3d_ransac_cert.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -107,3 +107,32 @@ def ransac(cams, xy, undistort=True, min_cams=2, threshold=0.5, init_best=200.0)
                          ctypes.c_double(threshold), ctypes.c_double(init_best), _p(p3d), _p(picked),
                          _p(xyp), _p(err), _p(sub), _p(nev)))
     return p3d, picked.view(np.bool_), xyp, err, sub, nev
+
+
+def cert_tables(cams):
+    """Pair-certificate tables of csrc/m3d_cert.h: (ok_mask, inv_mf (C,), E (pairs, 10))."""
+    C = len(cams)
+    ok = ctypes.c_int32(0)
+    inv = np.zeros(max(C, 1))
+    E = np.zeros((max(C * (C - 1) // 2, 1), 10))
+    _ok(load().hh_cert(cam_structs(cams), C, ctypes.byref(ok), _p(inv), _p(E)))
+    return ok.value, inv[:C], E[:C * (C - 1) // 2]
+
+
+def ransac_cert(cams, xy, undistort=True, min_cams=2, threshold=0.5, init_best=200.0, use_cert=True,
+                return_solved=False):
+    """The pruned subset search (csrc/m3d_ransac_cert.cuh ransac_cert_point) on the host."""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    C, n = len(cams), xy.shape[1]
+    p3d = np.empty((n, 3))
+    picked = np.empty((C, n, 1), dtype=np.uint8)
+    xyp = np.empty((C, n, 2))
+    err = np.empty(n)
+    sub = np.empty(n, dtype=np.int32)
+    nev = np.empty(n, dtype=np.int32)
+    solved = np.empty(n, dtype=np.int32)
+    _ok(load().hh_ransac_cert(cam_structs(cams), C, _p(xy), ctypes.c_int64(n), int(undistort), int(min_cams),
+                              ctypes.c_double(threshold), ctypes.c_double(init_best), int(use_cert), _p(p3d),
+                              _p(picked), _p(xyp), _p(err), _p(sub), _p(nev), _p(solved)))
+    res = (p3d, picked.view(np.bool_), xyp, err, sub, nev)
+    return res + (solved,) if return_solved else res

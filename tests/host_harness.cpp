@@ -13,6 +13,8 @@
 #include "../macaque_3d_pose_estimation_b200/csrc/m3d_math.cuh"
 #include "../macaque_3d_pose_estimation_b200/csrc/m3d_point.cuh"
 #include "../macaque_3d_pose_estimation_b200/csrc/m3d_rig.h"
+#include "../macaque_3d_pose_estimation_b200/csrc/m3d_cert.h"
+#include "../macaque_3d_pose_estimation_b200/csrc/m3d_ransac_cert.cuh"
 
 using namespace m3d;
 
@@ -269,6 +271,68 @@ int hh_ransac(const m3d_cam* cams, int C, const double* xy, int64_t N, int undis
   ransac_all<F, P>(rig, xy, N, undistort, min_cams, thr, init_best, p3d, picked, xy_picked, err, subset, neval)
   DISPATCH(rig, CALL);
 #undef CALL
+  return 0;
+}
+
+// pair-certificate tables of the pruned subset search (csrc/m3d_cert.h): inv_mf (C), E (pairs, 10)
+int hh_cert(const m3d_cam* cams, int C, int32_t* ok_mask, double* inv_mf, double* E) {
+  RigDev rig;
+  std::string why = build_rig(cams, C, &rig);
+  if (!why.empty()) {
+    g_err = why;
+    return -1;
+  }
+  static CertDev cert;
+  build_cert(rig, &cert);
+  *ok_mask = cert.ok_mask;
+  for (int c = 0; c < C; ++c) inv_mf[c] = cert.inv_mf[c];
+  const int np = C * (C - 1) / 2;
+  for (int p = 0; p < np; ++p)
+    for (int j = 0; j < 10; ++j) E[10 * p + j] = cert.E[p][j];
+  return 0;
+}
+
+// the pruned subset search of k_ransac_cert, point by point (the same ransac_cert_point the kernel runs)
+int hh_ransac_cert(const m3d_cam* cams, int C, const double* xy, int64_t N, int undistort, int min_cams,
+                   double threshold, double init_best, int use_cert, double* p3d, uint8_t* picked,
+                   double* xy_picked, double* err, int32_t* subset, int32_t* neval, int32_t* n_solved) {
+  RigDev rig;
+  std::string why = build_rig(cams, C, &rig);
+  if (!why.empty()) {
+    g_err = why;
+    return -1;
+  }
+  if (rig.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM)) {
+    g_err = "hh_ransac_cert: rational / thin-prism rigs are not handled by the pruned search";
+    return -1;
+  }
+  static CertDev cert;
+  build_cert(rig, &cert);
+  static const CumBinom cumb = make_cumbinom();
+  const bool po = (rig.flags & RIG_HAS_NONPINHOLE) == 0;
+  for (int64_t n = 0; n < N; ++n) {
+    XY raw[M3D_MAXC];
+    for (int c = 0; c < C; ++c) {
+      raw[c].x = xy[2 * ((int64_t)c * N + n)];
+      raw[c].y = xy[2 * ((int64_t)c * N + n) + 1];
+    }
+    CertOut o;
+    if (po) ransac_cert_point<true, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
+    else ransac_cert_point<false, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
+    p3d[3 * n] = o.X;
+    p3d[3 * n + 1] = o.Y;
+    p3d[3 * n + 2] = o.Z;
+    err[n] = o.err;
+    subset[n] = o.s_sel;
+    neval[n] = o.neval;
+    if (n_solved) n_solved[n] = o.n_solved;
+    for (int c = 0; c < C; ++c) {
+      const bool in = (o.sel >> (C - 1 - c)) & 1u;
+      picked[(int64_t)c * N + n] = in ? 1 : 0;
+      xy_picked[2 * ((int64_t)c * N + n)] = in ? raw[c].x : NAN;
+      xy_picked[2 * ((int64_t)c * N + n) + 1] = in ? raw[c].y : NAN;
+    }
+  }
   return 0;
 }
 

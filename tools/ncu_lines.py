@@ -47,7 +47,11 @@ def main():
     rep, ksub = sys.argv[1], sys.argv[2]
     npts = float(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else 1.0
     lines = disasm_lines(ksub)
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+    flt = []
+    for a in sys.argv:
+        if a.startswith("--kernel="):          # demangled-name regex when the report holds several kernels
+            flt = ["-k", "regex:" + a[len("--kernel="):]]
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + flt,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = rows[1]
