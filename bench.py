@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 multi-view 3D reconstruction hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload dlt|ransac] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload ransac|dlt] [--impl reference]
 
 metric  : triangulated joint-instances/sec (BASELINE.json)
-workload: "dlt"    = BASELINE config 2: 8-view undistort + DLT triangulate + mean reprojection
-                     error, 4 macaques x 17 joints x 1M frames = 6.8e7 joint-instances per GPU
-          "ransac" = BASELINE config 3: 8-view triangulate_ransac (all subsets, min 2 views),
-                     20 % outlier detections, frame-sharded
-A step is one pass of the hot path over the whole resident batch.  Inputs (8.7 GB for
-"dlt") are far larger than the 126 MB L2, so no flush is needed between iterations.
-N > 1: one process per GPU (torchrun), weak scaling (each rank owns its own frame chunk of
-the same size), no data-path collective; the NCCL gather of the 3D results to rank 0 is
-timed separately ("gather").
+workload: "ransac" (default, the configuration the north-star target is quoted on) = BASELINE
+                     config 3: 8-view triangulate_ransac (all camera subsets, min 2 views), 20 %
+                     outlier 2D detections, 4 macaques x 17 joints x 1M frames per GPU, frame-sharded
+                     in round-robin tiles; the NCCL gather of the 3D results to rank 0 runs per tile
+                     round INSIDE the timed step, overlapped with the next round's kernels
+          "dlt"    = BASELINE config 2: 8-view undistort + DLT triangulate + mean reprojection
+                     error, 4 macaques x 17 joints x 1M frames per GPU (no collective on this path:
+                     every rank returns its own frame range)
+The other workload is measured in the same run and reported as a complete second object
+("cfg2" / "cfg3": value, roofline, e2e, cpu_baseline).
+A step is one pass of the hot path over the whole resident batch (inputs of 8.7 GB per GPU are far
+larger than the 126 MB L2, so no flush is needed between iterations).  N > 1: one process per GPU
+(torchrun), weak scaling (each rank owns the same number of frames).
 
-`--impl reference` times the CPU port of the reference's NumPy/OpenCV path (oracle/) on
-the host cores for the same metric.
+`--impl reference` times the loop-faithful CPU port of the reference's NumPy/OpenCV path (oracle/)
+on all host cores for the same metric and workload; its `config` states the sample it really ran.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,6 +35,10 @@ sys.path.insert(0, ROOT)
 
 HBM_FALLBACK_GBS = 6650.0
 BYTES_PER_INSTANCE = {"dlt": lambda C: 16 * C + 32, "ransac": lambda C: 33 * C + 32}
+ANIMALS, JOINTS = 4, 17
+NAMES = {"dlt": "cfg2: %d-view undistort + DLT triangulate + mean reprojection_error, 4 macaques x 17 joints",
+         "ransac": "cfg3: %d-view triangulate_ransac (all camera subsets, min_cams=2), 20%% outlier detections, "
+                   "4 macaques x 17 joints"}
 
 
 def measured_peaks():
@@ -53,6 +62,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.windows = []
 
     def start(self):
         try:
@@ -70,8 +80,8 @@ class ClockSampler:
             self.lines.append((time.time(), line.strip()))
 
     def mark(self, t0, t1):
-        """wall-clock window of the timed region: only samples inside it are reported"""
-        self.window = (t0, t1)
+        """wall-clock window of a timed region: only samples inside the windows are reported"""
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
@@ -83,8 +93,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        win = getattr(self, "window", None)
-        inside = [ln for (t, ln) in self.lines if win and win[0] - 0.02 <= t <= win[1] + 0.02]
+        inside = [ln for (t, ln) in self.lines if any(a - 0.02 <= t <= b + 0.02 for a, b in self.windows)]
         use = inside if len(inside) >= 2 else [ln for (_, ln) in self.lines]
         for ln in use:
             parts = [p.strip() for p in ln.split(",")]
@@ -109,6 +118,7 @@ class ClockSampler:
 
 def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, device):
     import torch
+    from macaque_3d_pose_estimation_b200 import synth
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     f64 = torch.float64
@@ -127,8 +137,9 @@ def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, devi
     X = (root[:, :, None, :] + skel[None]).reshape(-1, 3).contiguous()
     del root
     xy = cg.project(X)                                         # our own projection kernel
+    del X
     C, N = xy.shape[0], xy.shape[1]
-    W, H = synth_image_size()
+    W, H = synth.IMG_SIZE
     for c in range(C):                                         # plane by plane: bounded temporaries
         # a camera does not detect what falls outside its frame (also keeps the polynomial
         # distortion model inside its monotone range)
@@ -140,7 +151,7 @@ def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, devi
             xy[c] += o[:, None] * torch.randn((N, 2), generator=g, device=device, dtype=f64) * 60.0
         m = torch.rand((N,), generator=g, device=device) < 0.1
         xy[c][m] = float("nan")
-    return X, xy
+    return xy
 
 
 # ------------------------------------------------------------------------------------------
@@ -149,7 +160,6 @@ def make_device_workload(cg, n_frames, n_animals, n_joints, seed, workload, devi
 
 def _cpu_chunk(args):
     dicts, p2d, workload = args
-    import numpy as np
     from oracle import cameragroup as og
     from oracle import fixtures
     cams = fixtures.cams_from_dicts(dicts)
@@ -161,382 +171,162 @@ def _cpu_chunk(args):
     return p2d.shape[1]
 
 
-def cpu_workload(workload, n_points, seed, n_cams=8):
+def cpu_workload(workload, n_frames, seed, n_cams=8):
+    """(rig dicts, (C, n_frames * 4 * 17, 2)): the numpy twin of make_device_workload (same rig, same
+    walk / skeleton / in-frame / noise / outlier / missing-view model), generated on the host."""
     import numpy as np
     from macaque_3d_pose_estimation_b200 import synth
     from oracle import cameragroup as og
     from oracle import fixtures
-    dicts = synth.make_rig(n_cams, "pinhole", seed=seed)
+    dicts = synth.make_rig(n_cams, "pinhole", seed=20261018 + 2)
     cams = fixtures.cams_from_dicts(dicts)
-    n_frames = max(1, n_points // (2 * 17))
-    X = synth.make_tracks(n_frames, 2, seed=seed).reshape(-1, 3)[:n_points]
-    p2d = synth.corrupt(og.project(cams, X), seed=seed, p_outlier=0.2 if workload == "ransac" else 0.0,
-                        p_missing=0.1)
-    return dicts, p2d
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array([-600.0, -600.0, 0.0]), np.array([600.0, 600.0, 800.0])
+    span = hi - lo
+    root = lo + rng.random((ANIMALS, 3)) * span + np.cumsum(rng.normal(0, 15.0, (n_frames, ANIMALS, 3)), axis=0)
+    root = lo + np.abs(span - np.abs((root - lo) % (2 * span) - span))
+    X = (root[:, :, None, :] + rng.normal(0, 120.0, (ANIMALS, JOINTS, 3))[None]).reshape(-1, 3)
+    xy = og.project(cams, X)
+    W, H = synth.IMG_SIZE
+    N = xy.shape[1]
+    for c in range(n_cams):
+        off = (xy[c, :, 0] < 0) | (xy[c, :, 0] > W) | (xy[c, :, 1] < 0) | (xy[c, :, 1] > H)
+        xy[c][off] = np.nan
+        xy[c] += rng.normal(0, 0.3, (N, 2))
+        if workload == "ransac":
+            o = rng.random(N) < 0.2
+            xy[c] += o[:, None] * rng.normal(0, 60.0, (N, 2))
+        xy[c][rng.random(N) < 0.1] = np.nan
+    return dicts, xy
 
 
-def time_cpu(workload, n_points, procs, seed=20261018, n_cams=8):
-    """joint-instances/s of the loop-faithful port on `procs` host processes."""
-    import numpy as np
-    dicts, p2d = cpu_workload(workload, n_points, seed, n_cams)
-    n = p2d.shape[1]
-    if procs <= 1:
-        _cpu_chunk((dicts, p2d[:, :8], workload))              # warm caches / imports
+class CpuPool:
+    """A persistent spawn pool for the all-core timings (created once, warmed once)."""
+
+    def __init__(self, procs, workload, n_cams):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs)
+        dicts, p2d = cpu_workload(workload, 1, 1, n_cams)
+        self.pool.map(_cpu_chunk, [(dicts, p2d[:, :8].copy(), workload)] * procs)   # spawn + import warm-up
+
+    def run(self, dicts, p2d, workload):
+        import numpy as np
+        chunks = np.array_split(np.arange(p2d.shape[1]), self.procs)
+        jobs = [(dicts, np.ascontiguousarray(p2d[:, c]), workload) for c in chunks if c.size]
         t0 = time.perf_counter()
-        _cpu_chunk((dicts, p2d, workload))
-        return n / (time.perf_counter() - t0), n
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    chunks = np.array_split(np.arange(n), procs)
-    jobs = [(dicts, np.ascontiguousarray(p2d[:, c]), workload) for c in chunks if c.size]
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_chunk, [(dicts, p2d[:, :8].copy(), workload)] * procs)   # spawn + import warm-up
-        t0 = time.perf_counter()
-        pool.map(_cpu_chunk, jobs)
-        dt = time.perf_counter() - t0
-    return n / dt, n
+        self.pool.map(_cpu_chunk, jobs)
+        return p2d.shape[1] / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def time_cpu_single(workload, n_frames, seed=20261018, n_cams=8):
+    dicts, p2d = cpu_workload(workload, n_frames, seed, n_cams)
+    _cpu_chunk((dicts, p2d[:, :8], workload))                  # warm caches / imports
+    t0 = time.perf_counter()
+    _cpu_chunk((dicts, p2d, workload))
+    return p2d.shape[1] / (time.perf_counter() - t0), p2d.shape[1]
+
+
+CPU_SAMPLE_FRAMES = {"dlt": 500, "ransac": 25}                 # single core: ~1.5 s / ~18 s
+CPU_POOL_FRAMES_PER_PROC = {"dlt": 250, "ransac": 8}           # all cores: ~1 s / ~6 s per step
+
+
+def cpu_baseline(workload, n_cams, with_all_cores):
+    v, n = time_cpu_single(workload, CPU_SAMPLE_FRAMES[workload], n_cams=n_cams)
+    out = {"value": v, "unit": "joint-instances/s", "cores": 1, "kind": "port",
+           "sample": "%d joint-instances (%d frames x 4 animals x 17 joints, the bench rig and corruption model), "
+                     "loop-faithful NumPy/OpenCV port of the reference (oracle/cameragroup.py *_loops)"
+                     % (n, CPU_SAMPLE_FRAMES[workload])}
+    if with_all_cores:
+        procs = max(1, min(os.cpu_count() or 1, 64))
+        pool = CpuPool(procs, workload, n_cams)
+        try:
+            dicts, p2d = cpu_workload(workload, CPU_POOL_FRAMES_PER_PROC[workload] * procs, 20261018 + 7, n_cams)
+            out["all_cores"] = {"value": pool.run(dicts, p2d, workload), "cores": procs,
+                                "sample": "%d joint-instances over %d spawn processes" % (p2d.shape[1], procs)}
+        finally:
+            pool.close()
+    return out
+
+
+def config_dict(workload, C, frames_per_gpu, n_gpus, extra=None):
+    d = {"workload": NAMES[workload] % C, "cameras": C, "camera_model": "pinhole(5 coeff)",
+         "joint_instances_per_gpu": int(frames_per_gpu * ANIMALS * JOINTS), "frames_per_gpu": int(frames_per_gpu),
+         "animals": ANIMALS, "joints": JOINTS, "missing_views": 0.1,
+         "outliers": 0.2 if workload == "ransac" else 0.0,
+         "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": "frame-sharded dp%d" % n_gpus}
+    if extra:
+        d.update(extra)
+    return d
 
 
 def run_reference(args):
-    """--impl reference: the CPU port on all host cores, same metric / config keys."""
+    """--impl reference: the CPU port on all host cores, same metric and workload; every step is a
+    bounded sample of the workload (stated in `config` and `cpu_baseline.sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    sample = 2 * 17 * (1000 if args.workload == "dlt" else 6) * max(1, procs // 2)
+    wl = args.workload
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    frames = CPU_POOL_FRAMES_PER_PROC[wl] * procs
+    pool = CpuPool(procs, wl, args.cameras)
     vals = []
+    n = 0
     t_all = time.perf_counter()
-    for i in range(args.steps):
-        v, n = time_cpu(args.workload, sample, procs, n_cams=args.cameras)
-        vals.append(v)
-        if time.perf_counter() - t_all > 240:
-            break
+    try:
+        for i in range(args.warmup + args.steps):
+            dicts, p2d = cpu_workload(wl, frames, 20261018 + 11 + i, args.cameras)
+            n = p2d.shape[1]
+            v = pool.run(dicts, p2d, wl)
+            if i >= args.warmup:
+                vals.append(v)
+            if time.perf_counter() - t_all > 200 and vals:
+                break
+    finally:
+        pool.close()
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "triangulated joint-instances/sec", "value": value,
         "unit": "joint-instances/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
         "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, args.cameras, args.frames * 4 * 17),     # the workload of our arm; see cpu_baseline.sample
+        "config": config_dict(wl, args.cameras, frames, args.gpus,
+                              {"parallelism": "%d host processes" % procs,
+                               "l2_policy": "n/a (CPU)",
+                               "note": "bounded sample of the workload of the GPU arm: same rig, corruption model, "
+                                       "animals x joints; %d frames per step instead of %d per GPU"
+                                       % (frames, default_frames(wl))}),
         "cpu_baseline": {"value": value, "unit": "joint-instances/s", "cores": procs, "kind": "port",
-                         "sample": "%d joint-instances per step (cfg-1 rig: pinhole cameras, 2 animals x 17 "
-                                   "joints), loop-faithful NumPy/OpenCV port of the reference in oracle/, "
-                                   "%d spawn processes" % (n, procs)},
+                         "sample": "%d joint-instances per step, loop-faithful NumPy/OpenCV port of the reference "
+                                   "(oracle/), %d spawn processes (one persistent pool)" % (n, procs)},
         "e2e": {"value": value, "unit": "joint-instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def config_dict(args, C, n_per_gpu):
-    names = {"dlt": "cfg2: %d-view undistort + DLT triangulate + mean reprojection_error, 4 macaques x 17 joints",
-             "ransac": "cfg3: %d-view triangulate_ransac (all camera subsets, min_cams=2), 20%% outlier detections"}
-    return {"workload": names[args.workload] % C, "cameras": C, "camera_model": "pinhole(5 coeff)",
-            "joint_instances_per_gpu": int(n_per_gpu), "frames_per_gpu": int(args.frames),
-            "animals": 4, "joints": 17, "missing_views": 0.1,
-            "outliers": 0.2 if args.workload == "ransac" else 0.0,
-            "l2_policy": "inputs larger than L2 (no flush needed)", "parallelism": "frame-sharded dp%d" % args.gpus}
+def default_frames(workload):
+    return 1000000
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 
-def run_gpu(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as ge
-    ge.build()
-    from macaque_3d_pose_estimation_b200 import _lib, synth
-    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    lib = _lib.require_gpu()
-
-    C, A, J = args.cameras, 4, 17
-    F = args.frames
-    seed = 20261018 + 2 + rank
-    cg = CameraGroup.from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2))
-    cg.device = local
-    X, xy = make_device_workload(cg, F, A, J, seed, args.workload, device)
-    del X
-    N = xy.shape[1]
-    p3d = torch.empty((N, 3), dtype=torch.float64, device=device)
-    err = torch.empty((N,), dtype=torch.float64, device=device)
-    picked = torch.empty((C, N), dtype=torch.uint8, device=device) if args.workload == "ransac" else None
-    xyp = torch.empty((C, N, 2), dtype=torch.float64, device=device) if args.workload == "ransac" else None
-    nev = torch.empty((N,), dtype=torch.int32, device=device) if args.workload == "ransac" else None
-    rig = cg._rig(local)
-    stream = torch.cuda.current_stream(device)
-    sp = lambda t: None if t is None else t.data_ptr()
-
-    def step():
-        if args.workload == "dlt":
-            rc = lib.m3d_triangulate_error(rig.handle, xy.data_ptr(), N, 1, p3d.data_ptr(), err.data_ptr(),
-                                           stream.cuda_stream)
-        else:
-            rc = lib.m3d_triangulate_ransac(rig.handle, xy.data_ptr(), N, 1, 2, 0.5, 200.0, p3d.data_ptr(),
-                                            sp(picked), sp(xyp), err.data_ptr(), None, sp(nev),
-                                            stream.cuda_stream)
-        _lib.check(rc, "bench step")
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    launches0 = lib.m3d_launch_count()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    t_wall0 = time.time()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    sampler.mark(t_wall0, time.time())
-    ms = e0.elapsed_time(e1)
-    launches = lib.m3d_launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms / args.steps
-    value = world * N / (ms_per_step * 1e-3)
-
-    # gather of the 3D results to rank 0 (the only collective of the path), timed separately
-    gather_ms = None
-    if world > 1:
-        from macaque_3d_pose_estimation_b200 import sharding
-        small = torch.zeros((world * 8,), dtype=torch.float64, device=device)
-        dist.all_reduce(small)                                 # communicator set-up outside the timing
-        out = sharding.gather_results([p3d, err], F, dst=0)    # one untimed gather (NCCL warm-up)
-        del out
-        torch.cuda.synchronize()
-        dist.barrier()
-        g0 = torch.cuda.Event(enable_timing=True)
-        g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        out = sharding.gather_results([p3d, err], F, dst=0)
-        g1.record()
-        torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather_ms = float(tg.item())
-        del out
-
-    peak, peak_kind = measured_peaks()
-    bpi = BYTES_PER_INSTANCE[args.workload](C)
-    achieved = bpi * N / (ms_per_step * 1e-3) / 1e9            # per-GPU kernel, GB/s
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind + " copy bandwidth",
-                "kernel": "k_triangulate<undistort,err>" if args.workload == "dlt" else "k_ransac",
-                "algorithmic_bytes_per_instance": bpi,
-                "note": "path is fp64-ALU bound at reference precision (SURVEY 7); see fp64"}
-    try:   # DRAM traffic per launch from the committed ncu capture (profiles/traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
-        roofline["traffic"] = tj["dram_bytes_per_instance"] * N
-        roofline["traffic_source"] = tj["source"]
-    except Exception:
-        pass
-    tf = ctypes_double()
-    if rank == 0 and lib.m3d_probe_fp64_tflops(local, ctypes_byref(tf)) == 0:
-        roofline["fp64_peak_tflops_measured"] = tf.value
-        try:   # the binding bound: fp64 pipe slots (one per fp64 instruction and lane) from the committed ncu capture
-            per = float(tj["fp64_thread_instr_per_instance"])
-            ach = per * N / (ms_per_step * 1e-3) / 1e12
-            roofline["fp64"] = {"thread_instr_per_instance": per, "achieved": ach, "peak": tf.value / 2.0,
-                                "unit": "T fp64 instr/s (per GPU)", "frac": ach / (tf.value / 2.0),
-                                "source": tj.get("fp64_source")}
-        except Exception:
-            pass
-    extra = {"mean_valid_views": float((~torch.isnan(xy[:, :, 0])).double().mean().item() * C)}
-    if args.workload == "ransac":
-        extra["mean_subsets_per_point"] = float(nev.double().mean().item())
-        extra["selected_fraction"] = float((~torch.isnan(p3d[:, 0])).double().mean().item())
-
-    # ---- e2e: host buffers through the C-ABI host pipeline (H2D + kernel + D2H per step), every
-    # rank streams its own shard concurrently ----
-    # N = 1: the whole workload; N > 1: a 2e7-instance slice per rank (bounds the pinned host
-    # memory of 8 concurrent ranks), reported in joint_instances_per_gpu
-    n_e2e = min(N, args.e2e_points) if args.e2e_points > 0 else (N if world == 1 else min(N, 20000000))
-    e2e = None
-    try:
-        if args.no_e2e:
-            raise RuntimeError("skipped (--no-e2e)")
-        numa = bind_to_gpu_numa_node(local)     # host buffers on the memory next to this rank's GPU
-        h_xy = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True)
-        h_xy.copy_(xy[:, :n_e2e])
-        h_p3d = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
-        h_err = torch.empty((n_e2e,), dtype=torch.float64, pin_memory=True)
-        h_pick = torch.empty((C, n_e2e), dtype=torch.uint8, pin_memory=True) if args.workload == "ransac" else None
-        h_xyp = torch.empty((C, n_e2e, 2), dtype=torch.float64, pin_memory=True) if args.workload == "ransac" else None
-
-        def e2e_step():
-            if args.workload == "dlt":
-                rc = lib.m3d_triangulate_error_host(rig.handle, h_xy.data_ptr(), n_e2e, 1, h_p3d.data_ptr(),
-                                                    h_err.data_ptr())
-            else:
-                rc = lib.m3d_triangulate_ransac_host(rig.handle, h_xy.data_ptr(), n_e2e, 1, 2, 0.5, 200.0,
-                                                     h_p3d.data_ptr(), sp(h_pick), sp(h_xyp), h_err.data_ptr(),
-                                                     None, None)
-            _lib.check(rc, "e2e step")
-        e2e_step()
-        torch.cuda.synchronize()
-        ke = max(1, min(args.steps, 5))
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            e2e_step()
-        dt = (time.perf_counter() - t0) / ke
-        if world > 1:
-            td = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-            dt = float(td.item())
-        # the pipeline's output equals the resident run
-        assert torch.equal(h_p3d.nan_to_num(), p3d[:n_e2e].cpu().nan_to_num())
-        d2h = n_e2e * 32 + (n_e2e * C * 17 if args.workload == "ransac" else 0)
-        e2e = {"value": world * n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 16,
-               "d2h_bytes_per_step": d2h, "joint_instances_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
-               "api": "m3d_triangulate_%s_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"
-                      % ("error" if args.workload == "dlt" else "ransac"), "n_gpus": world,
-               "host_numa_node": numa}
-        del h_xy, h_p3d, h_err
-    except Exception as ex:  # pragma: no cover
-        e2e = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:200]}
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- secondary line: BASELINE config 3 (subset RANSAC, 20 % outliers) on a 1e5-frame slice ----
-    if args.workload == "dlt" and not args.no_ransac_extra:
-        try:
-            del xy
-            torch.cuda.empty_cache()
-            Fr = 100000
-            _, xyr = make_device_workload(cg, Fr, A, J, seed + 100, "ransac", device)
-            Nr = xyr.shape[1]
-            r3 = torch.empty((Nr, 3), dtype=torch.float64, device=device)
-            re_ = torch.empty((Nr,), dtype=torch.float64, device=device)
-            rp = torch.empty((C, Nr), dtype=torch.uint8, device=device)
-            rx = torch.empty((C, Nr, 2), dtype=torch.float64, device=device)
-            rn = torch.empty((Nr,), dtype=torch.int32, device=device)
-
-            def rstep():
-                _lib.check(lib.m3d_triangulate_ransac(rig.handle, xyr.data_ptr(), Nr, 1, 2, 0.5, 200.0, r3.data_ptr(),
-                                                      rp.data_ptr(), rx.data_ptr(), re_.data_ptr(), None, rn.data_ptr(),
-                                                      stream.cuda_stream), "ransac step")
-            for _ in range(3):
-                rstep()
-            torch.cuda.synchronize()
-            r0 = torch.cuda.Event(enable_timing=True)
-            r1 = torch.cuda.Event(enable_timing=True)
-            r0.record(stream)
-            for _ in range(5):
-                rstep()
-            r1.record(stream)
-            torch.cuda.synchronize()
-            rms = r0.elapsed_time(r1) / 5
-            extra["ransac"] = {
-                "workload": "cfg3: 8-view triangulate_ransac (all camera subsets, min_cams=2), 20% outlier detections",
-                "value": Nr / (rms * 1e-3), "unit": "joint-instances/s (one GPU)", "joint_instances": Nr,
-                "ms_per_step": rms, "mean_subsets_per_point": float(rn.double().mean().item()),
-                "roofline_frac_hbm": 296 * Nr / (rms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_instance": 296}
-        except Exception as ex:  # pragma: no cover
-            extra["ransac"] = {"error": str(ex)[:200]}
-        # ---- step-4 2D Viterbi filter on the series of the same recording shape (SURVEY 8f-2) ----
-        try:
-            from macaque_3d_pose_estimation_b200 import filter2d
-            Sv, Fv = A * C * J, 20000
-            det = torch.from_numpy(np.ascontiguousarray(
-                synth.make_detection_series(Fv, 32, 1, seed).transpose(1, 0, 2, 3))).to(device)
-            det = det.repeat((Sv + 31) // 32, 1, 1, 1)[:Sv].contiguous()
-            for _ in range(2):
-                filter2d.viterbi_series(det, 3, 25.0, 0.3)
-            torch.cuda.synchronize()
-            v0 = torch.cuda.Event(enable_timing=True)
-            v1 = torch.cuda.Event(enable_timing=True)
-            v0.record()
-            for _ in range(3):
-                filter2d.viterbi_series(det, 3, 25.0, 0.3)
-            v1.record()
-            torch.cuda.synchronize()
-            vms = v0.elapsed_time(v1) / 3
-            extra["viterbi_filter"] = {
-                "workload": "step-4 2D Viterbi filter (n_back 3, offset_threshold 25, score_threshold 0.3), %d series "
-                            "(animals x cameras x joints) x %d frames" % (Sv, Fv),
-                "value": Sv * Fv / (vms * 1e-3), "unit": "series-frames/s (one GPU)", "ms_per_step": vms}
-        except Exception as ex:  # pragma: no cover
-            extra["viterbi_filter"] = {"error": str(ex)[:200]}
-
-    # ---- CPU baseline: loop-faithful port, one core, bounded sample ---------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        n_cpu = 34000 if args.workload == "dlt" else 340
-        v, n = time_cpu(args.workload, n_cpu, 1, n_cams=C)
-        cpu = {"value": v, "unit": "joint-instances/s", "cores": 1, "kind": "port",
-               "sample": "%d joint-instances of the cfg-1 rig (8 pinhole cameras), loop-faithful NumPy/OpenCV "
-                         "port of the reference (oracle/cameragroup.py *_loops)" % n}
-
-    line = {
-        "metric": "triangulated joint-instances/sec", "value": value, "unit": "joint-instances/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, C, N), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(launches), "clocks": clocks,
-    }
-    if gather_ms is not None:
-        line["gather"] = {"ms": gather_ms, "bytes_to_rank0": int((world - 1) * N * 32),
-                          "what": "torch.distributed.gather (NCCL) of p3d+err to rank 0"}
-    line.update(extra)
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def synth_image_size():
-    from macaque_3d_pose_estimation_b200 import synth
-    return synth.IMG_SIZE
-
-
-def ctypes_double():
-    import ctypes
-    return ctypes.c_double(0.0)
-
-
-def ctypes_byref(x):
-    import ctypes
-    return ctypes.byref(x)
+class Ctx:
+    pass
 
 
 def bind_to_gpu_numa_node(local):
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
-    buffers allocated afterwards are local to that GPU's PCIe root (with 8 ranks the H2D streams
-    otherwise cross the socket interconnect).  Returns the node or None; never fails."""
+    buffers allocated afterwards are local to that GPU's PCIe root.  Returns the node or None
+    (platform does not expose one); never fails."""
     try:
+        import torch
         p = torch.cuda.get_device_properties(local)
         bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
@@ -555,22 +345,393 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
+def sync_all(cx):
+    import torch
+    torch.cuda.synchronize()
+    if cx.world > 1:
+        cx.dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(cx, x):
+    import torch
+    if cx.world == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64, device=cx.device)
+    cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_steps(cx, step, steps, warmup):
+    """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launch
+    stream, max over ranks.  Returns (ms per step, launches in the timed region)."""
+    import torch
+    for _ in range(max(warmup, 3)):
+        step()
+    sync_all(cx)
+    launches0 = cx.lib.m3d_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(cx.stream)
+    for _ in range(steps):
+        step()
+    e1.record(cx.stream)
+    torch.cuda.synchronize()
+    if cx.sampler is not None:
+        cx.sampler.mark(t_wall0, time.time())
+    ms = e0.elapsed_time(e1)
+    launches = cx.lib.m3d_launch_count() - launches0
+    ms = max_over_ranks(cx, ms)
+    if cx.world > 1:
+        cx.dist.barrier()
+    return ms / steps, int(launches)
+
+
+def kernel_breakdown(cx, step, reps=2):
+    """Per-kernel device time of `reps` extra steps (CUDA events around every launch, on the launch
+    stream, inside the library: m3d_profile_enable / m3d_profile_read)."""
+    import torch
+    buf = ctypes.create_string_buffer(1 << 14)
+    cx.lib.m3d_profile_enable(1)
+    cx.lib.m3d_profile_read(buf, len(buf))                     # clear
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    rc = cx.lib.m3d_profile_read(buf, len(buf))
+    cx.lib.m3d_profile_enable(0)
+    if rc != 0:
+        return {}
+    d = json.loads(buf.value.decode())
+    return {k: {"launches_per_step": v["launches"] / reps, "ms_per_launch": v["ms"] / max(1, v["launches"]),
+                "ms_per_step": v["ms"] / reps} for k, v in d.items()}
+
+
+def roofline_of(cx, workload, C, n_per_step, ms_per_step, kernels):
+    peak, peak_kind = measured_peaks()
+    bpi = BYTES_PER_INSTANCE[workload](C)
+    roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_kind": peak_kind + " copy bandwidth",
+            "algorithmic_bytes_per_instance": bpi, "traffic": None}
+    # the whole path (all kernels of a step): what the metric sees
+    path = bpi * n_per_step / (ms_per_step * 1e-3) / 1e9
+    if kernels:
+        name = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        kd = kernels[name]
+        n_launch = n_per_step / max(1.0, kd["launches_per_step"])
+        ach = bpi * n_launch / (kd["ms_per_launch"] * 1e-3) / 1e9
+        roof.update({"kernel": name, "achieved": ach, "frac": ach / peak,
+                     "kernel_ms_per_launch": kd["ms_per_launch"], "instances_per_launch": n_launch,
+                     "kernel_share_of_step": kd["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())})
+    else:
+        roof.update({"kernel": "whole step", "achieved": path, "frac": path / peak})
+    roof["path"] = {"achieved": path, "frac": path / peak,
+                    "what": "algorithmic bytes of a step / step time (all kernels, collective included)"}
+    roof["kernels"] = kernels
+    roof["note"] = ("the path is fp64-ALU bound at reference precision (SURVEY 7): 60 % of HBM would need more fp64 "
+                    "instructions per second than the B200 issues")
+    try:   # DRAM traffic per launch of the dominant kernel from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        if tj.get("kernel") == roof.get("kernel"):
+            roof["traffic"] = tj["dram_bytes_per_instance"] * roof.get("instances_per_launch", n_per_step)
+        roof["traffic_source"] = tj["source"]
+        tf = ctypes.c_double(0.0)
+        if cx.rank == 0 and cx.lib.m3d_probe_fp64_tflops(cx.local, ctypes.byref(tf)) == 0:
+            roof["fp64_peak_tflops_measured"] = tf.value
+            per = float(tj["fp64_thread_instr_per_instance"])
+            ach = per * n_per_step / (ms_per_step * 1e-3) / 1e12
+            roof["fp64"] = {"thread_instr_per_instance": per, "achieved": ach, "peak": tf.value / 2.0,
+                            "unit": "T fp64 instr/s (per GPU)", "frac": ach / (tf.value / 2.0),
+                            "source": tj.get("fp64_source")}
+    except Exception:
+        pass
+    return roof
+
+
+def copy_ceiling(cx, nbytes=1 << 30, reps=3):
+    """Plain pinned cudaMemcpyAsync H2D + D2H at once on two streams, every rank concurrently: the
+    ceiling the e2e numbers are read against.  Aggregate GB/s over all ranks."""
+    import torch
+    try:
+        h_in = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty((nbytes,), dtype=torch.uint8, device=cx.device)
+        d_out = torch.empty((nbytes,), dtype=torch.uint8, device=cx.device)
+        s1, s2 = torch.cuda.Stream(cx.device), torch.cuda.Stream(cx.device)
+        res = {}
+        for mode in ("h2d", "d2h", "duplex"):
+            best = None
+            for _ in range(reps + 1):
+                sync_all(cx)
+                t0 = time.perf_counter()
+                if mode in ("h2d", "duplex"):
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(h_in, non_blocking=True)
+                if mode in ("d2h", "duplex"):
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize()
+                dt = max_over_ranks(cx, time.perf_counter() - t0)
+                best = dt if best is None else min(best, dt)
+            mult = 2 if mode == "duplex" else 1
+            res[mode + "_gbs"] = cx.world * mult * nbytes / best / 1e9
+        res["what"] = ("pinned cudaMemcpyAsync of 1 GiB per direction and rank, all ranks at once, aggregate over "
+                       "ranks (duplex: both directions at once, sum of both)")
+        return res
+    except Exception as ex:  # pragma: no cover
+        return {"error": str(ex)[:200]}
+
+
+def e2e_run(cx, workload, xy_dev, n_e2e, ref_p3d, steps, f32):
+    """Same metric through the C-ABI host pipeline: pinned HOST buffers in, HOST buffers out, H2D +
+    kernels + D2H inside every timed call, every rank streaming its own shard at once."""
+    import torch
+    C = xy_dev.shape[0]
+    lib, rig = cx.lib, cx.rig
+    from macaque_3d_pose_estimation_b200 import _lib
+    sp = lambda t: None if t is None else t.data_ptr()
+    in_dt = torch.float32 if f32 else torch.float64
+    h_xy = torch.empty((C, n_e2e, 2), dtype=in_dt, pin_memory=True)
+    h_xy.copy_(xy_dev[:, :n_e2e])
+    h_p3d = torch.empty((n_e2e, 3), dtype=torch.float64, pin_memory=True)
+    h_err = torch.empty((n_e2e,), dtype=torch.float64, pin_memory=True)
+    h_pick = h_xyp = None
+    if workload == "ransac":
+        h_pick = torch.empty((C, n_e2e), dtype=torch.uint8, pin_memory=True)
+        h_xyp = torch.empty((C, n_e2e, 2), dtype=in_dt, pin_memory=True)
+    sfx = "_f32" if f32 else ""
+
+    def call():
+        if workload == "dlt":
+            fn = getattr(lib, "m3d_triangulate_error_host" + sfx)
+            rc = fn(rig.handle, h_xy.data_ptr(), n_e2e, 1, h_p3d.data_ptr(), h_err.data_ptr())
+        else:
+            fn = getattr(lib, "m3d_triangulate_ransac_host" + sfx)
+            rc = fn(rig.handle, h_xy.data_ptr(), n_e2e, 1, 2, 0.5, 200.0, h_p3d.data_ptr(), sp(h_pick), sp(h_xyp),
+                    h_err.data_ptr(), None, None)
+        _lib.check(rc, "e2e step")
+    call()
+    torch.cuda.synchronize()
+    ke = max(1, min(steps, 5))
+    sync_all(cx)
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        call()
+    dt = max_over_ranks(cx, (time.perf_counter() - t0) / ke)
+    if ref_p3d is not None:    # the pipeline's output equals the resident run (f64 input only)
+        assert torch.equal(h_p3d.nan_to_num(), ref_p3d[:n_e2e].cpu().nan_to_num()), "e2e result differs"
+    isz = 4 if f32 else 8
+    d2h = n_e2e * 32 + (n_e2e * C * (1 + 2 * isz) if workload == "ransac" else 0)
+    return {"value": cx.world * n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 2 * isz,
+            "d2h_bytes_per_step": d2h, "joint_instances_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
+            "input_dtype": "f32 (widened on the device)" if f32 else "f64",
+            "api": "m3d_triangulate_%s_host%s (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"
+                   % ("error" if workload == "dlt" else "ransac", sfx), "n_gpus": cx.world}
+
+
+def measure(cx, args, workload):
+    """One workload end to end: device-resident value, kernel breakdown / roofline, e2e, CPU baseline."""
+    import torch
+    from macaque_3d_pose_estimation_b200 import _lib, sharding
+    lib, rig, device, world, rank = cx.lib, cx.rig, cx.device, cx.world, cx.rank
+    C = args.cameras
+    F = args.frames if args.frames > 0 else default_frames(workload)
+    per = ANIMALS * JOINTS
+    N = F * per
+    seed = 20261018 + (2 if workload == "dlt" else 3) + 17 * rank
+    xy = make_device_workload(cx.cg, F, ANIMALS, JOINTS, seed, workload, device)
+    p3d = torch.empty((N, 3), dtype=torch.float64, device=device)
+    err = torch.empty((N,), dtype=torch.float64, device=device)
+    sp = lambda t: None if t is None else t.data_ptr()
+    extra = {"mean_valid_views": float((~torch.isnan(xy[:, :, 0])).double().mean().item() * C)}
+    out = {}
+
+    if workload == "dlt":
+        def step():
+            _lib.check(lib.m3d_triangulate_error(rig.handle, xy.data_ptr(), N, 1, p3d.data_ptr(), err.data_ptr(),
+                                                 cx.stream.cuda_stream), "bench step")
+        collective = None
+    else:
+        # this rank's tiles of the round-robin deal, stored tile by tile
+        rounds = max(1, args.rounds)
+        tile_frames = -(-F // rounds)
+        plan = sharding.TilePlan(F * world, world, tile_frames, per)
+        tiles = []
+        off = 0
+        for j in range(plan.rounds):
+            a, b = plan.tile_span(j * world + rank)
+            n = (b - a) * per
+            t = {"n": n, "off": off, "xy": xy[:, off:off + n].contiguous(),
+                 "picked": torch.empty((C, n), dtype=torch.uint8, device=device),
+                 "xyp": torch.empty((C, n, 2), dtype=torch.float64, device=device)}
+            tiles.append(t)
+            off += n
+        assert off == N
+        nev = torch.empty((N,), dtype=torch.int32, device=device)
+        rg = sharding.RoundGather(plan, [(3,), ()], torch.float64, device, dst=0, group=None) if world > 1 else None
+
+        def step():
+            for j, t in enumerate(tiles):
+                o, n = t["off"], t["n"]
+                if n:
+                    _lib.check(lib.m3d_triangulate_ransac(
+                        rig.handle, t["xy"].data_ptr(), n, 1, 2, 0.5, 200.0, p3d[o:o + n].data_ptr(),
+                        t["picked"].data_ptr(), t["xyp"].data_ptr(), err[o:o + n].data_ptr(), None,
+                        nev[o:o + n].data_ptr(), cx.stream.cuda_stream), "bench step")
+                if rg is not None:
+                    rg.add(j, [p3d[o:o + n], err[o:o + n]])
+            if rg is not None:
+                rg.finish()
+        collective = None if world == 1 else {
+            "what": "torch.distributed.gather (NCCL, async_op) of p3d + err to rank 0, one per tile round, issued "
+                    "inside the timed step and overlapped with the next round's kernels; rank 0 receives in "
+                    "global frame order", "rounds_per_step": plan.rounds,
+            "bytes_to_rank0_per_step": int((world - 1) * N * 32)}
+
+    ms_per_step, launches = timed_steps(cx, step, args.steps, args.warmup)
+    value = world * N / (ms_per_step * 1e-3)
+    if workload == "ransac" and world > 1:
+        # the same step without the collective: what the gather costs
+        rg_keep = rg
+        rg = None
+        ms_nc, _ = timed_steps(cx, step, max(2, args.steps // 2), 3)
+        rg = rg_keep
+        collective["ms_per_step_without_collective"] = ms_nc
+        collective["ms_per_step_with_collective"] = ms_per_step
+        if rank == 0:   # sharded result == this rank's own tiles where they land in the global arrays
+            res = rg.out
+            j, t = 0, tiles[0]
+            a, b = plan.tile_span(j * world + rank)
+            assert torch.equal(res[1][a * per:b * per], err[t["off"]:t["off"] + t["n"]]), "gathered rows differ"
+    kernels = kernel_breakdown(cx, step) if rank == 0 or world > 1 else {}
+    out["value"] = value
+    out["ms_per_step"] = ms_per_step
+    out["gpu_launches"] = launches
+    out["roofline"] = roofline_of(cx, workload, C, N, ms_per_step, kernels)
+    if workload == "ransac":
+        extra["mean_subsets_per_point"] = float(nev.double().mean().item())
+        extra["selected_fraction"] = float((~torch.isnan(p3d[:, 0])).double().mean().item())
+    if collective:
+        out["collective"] = collective
+
+    # ---- e2e through host buffers: the same per-GPU size at every N -------------------------
+    n_e2e = min(N, args.e2e_points)
+    if args.no_e2e:
+        out["e2e"] = {"value": None, "unit": "joint-instances/s", "error": "skipped (--no-e2e)"}
+    else:
+        try:
+            xy_flat = xy if workload == "dlt" else torch.cat([t["xy"] for t in tiles], dim=1)
+            out["e2e"] = e2e_run(cx, workload, xy_flat, n_e2e, p3d, args.steps, f32=False)
+            out["e2e"]["host_numa_node"] = cx.numa
+            out["e2e_f32"] = e2e_run(cx, workload, xy_flat, n_e2e, None, args.steps, f32=True)
+            del xy_flat
+        except Exception as ex:  # pragma: no cover
+            out["e2e"] = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:300]}
+    out["config"] = config_dict(workload, C, F, world)
+    out["extra"] = extra
+    del xy, p3d, err
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build_library()
+    from macaque_3d_pose_estimation_b200 import _lib, synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+
+    cx = Ctx()
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx.dist = dist
+    torch.cuda.set_device(cx.local)
+    cx.device = torch.device("cuda", cx.local)
+    cx.numa = bind_to_gpu_numa_node(cx.local)     # before any pinned allocation
+    if cx.world > 1:
+        dist.init_process_group("nccl", device_id=cx.device)
+        warm = torch.zeros((cx.world * 8,), dtype=torch.float64, device=cx.device)
+        dist.all_reduce(warm)                     # communicator set-up outside every timing
+    cx.lib = _lib.require_gpu()
+    cx.cg = CameraGroup.from_dicts(synth.make_rig(args.cameras, "pinhole", seed=20261018 + 2))
+    cx.cg.device = cx.local
+    cx.rig = cx.cg._rig(cx.local)
+    cx.stream = torch.cuda.current_stream(cx.device)
+    cx.sampler = ClockSampler(cx.local) if cx.rank == 0 else None
+    if cx.sampler:
+        cx.sampler.start()
+        time.sleep(0.25)
+
+    other = "dlt" if args.workload == "ransac" else "ransac"
+    head = measure(cx, args, args.workload)
+    second = None if args.only else measure(cx, args, other)
+    ceiling = None if args.no_e2e else copy_ceiling(cx)
+    clocks = cx.sampler.stop() if cx.sampler else None
+
+    if cx.rank != 0:
+        if cx.world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baselines (rank 0, N = 1 only): loop-faithful port, one core + all cores ---------
+    if cx.world == 1 and not args.no_cpu:
+        head["cpu_baseline"] = cpu_baseline(args.workload, args.cameras, True)
+        if second is not None:
+            second["cpu_baseline"] = cpu_baseline(other, args.cameras, True)
+
+    for obj in (head, second):
+        if obj is not None and ceiling is not None and obj["e2e"].get("value"):
+            obj["e2e"]["pcie_ceiling"] = ceiling
+            bytes_per_inst = (obj["e2e"]["h2d_bytes_per_step"] + obj["e2e"]["d2h_bytes_per_step"]) / \
+                obj["e2e"]["joint_instances_per_gpu"]
+            obj["e2e"]["moved_gbs"] = obj["e2e"]["value"] * bytes_per_inst / 1e9
+            if ceiling.get("duplex_gbs"):
+                obj["e2e"]["frac_of_duplex_ceiling"] = obj["e2e"]["moved_gbs"] / ceiling["duplex_gbs"]
+
+    line = {
+        "metric": "triangulated joint-instances/sec", "value": head["value"], "unit": "joint-instances/s",
+        "n_gpus": cx.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": head["config"], "roofline": head["roofline"], "cpu_baseline": head.get("cpu_baseline"),
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks,
+    }
+    for k in ("e2e_f32", "collective"):
+        if k in head:
+            line[k] = head[k]
+    line.update(head["extra"])
+    if second is not None:
+        key = "cfg2" if other == "dlt" else "cfg3"
+        sec = {k: second[k] for k in ("value", "ms_per_step", "gpu_launches", "config", "roofline", "e2e") if k in second}
+        sec["unit"] = "joint-instances/s"
+        for k in ("e2e_f32", "collective", "cpu_baseline"):
+            if k in second:
+                sec[k] = second[k]
+        sec.update(second["extra"])
+        line[key] = sec
+    print(json.dumps(line))
+    if cx.world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=["dlt", "ransac"], default="dlt")
+    ap.add_argument("--workload", choices=["dlt", "ransac"], default="ransac")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6 dlt, 2e5 ransac)")
-    ap.add_argument("--e2e-points", type=int, default=0, help="joint-instances of the e2e run (0 = all)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6)")
+    ap.add_argument("--rounds", type=int, default=16, help="tile rounds per step of the sharded RANSAC")
+    ap.add_argument("--e2e-points", type=int, default=20000000,
+                    help="joint-instances per GPU of the e2e run (the same at every N)")
     ap.add_argument("--cameras", type=int, default=8, help="cameras of the synthetic ring rig (BASELINE: 8; config 5: 16)")
+    ap.add_argument("--only", action="store_true", help="measure the headline workload only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-ransac-extra", action="store_true")
     args = ap.parse_args()
-    if args.frames <= 0:
-        args.frames = 1000000 if args.workload == "dlt" else 200000
     if args.impl == "reference":
         run_reference(args)
     else:

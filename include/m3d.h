@@ -160,6 +160,18 @@ int m3d_triangulate_ransac_host(const m3d_rig* rig, const double* xy_host, int64
                                 double init_best, double* p3d_host, uint8_t* picked_host,
                                 double* xy_picked_host, double* err_host,
                                 int32_t* subset_host, int32_t* neval_host);
+/* The same pipelines for float32 observations (the 2D pose network's native output): xy_host
+ * (C,N,2) float32 is widened to float64 on the device, every result is what the float64 entry point
+ * returns for the same (float32-representable) values; xy_picked_host (C,N,2) float32 is exact for
+ * the same reason.  Halves the host-to-device bytes of the call (reference callers hold float64
+ * arrays: kp2d.pickle after step 1's smoothing — they use the entry points above). */
+int m3d_triangulate_error_host_f32(const m3d_rig* rig, const float* xy_host, int64_t N,
+                                   int32_t undistort, double* p3d_host, double* err_host);
+int m3d_triangulate_ransac_host_f32(const m3d_rig* rig, const float* xy_host, int64_t N,
+                                    int32_t undistort, int32_t min_cams, double threshold,
+                                    double init_best, double* p3d_host, uint8_t* picked_host,
+                                    float* xy_picked_host, double* err_host, int32_t* subset_host,
+                                    int32_t* neval_host);
 /* cudaHostRegister / cudaHostUnregister for caller-owned numpy buffers. */
 int m3d_host_register(void* ptr, int64_t bytes);
 int m3d_host_unregister(void* ptr);
@@ -210,6 +222,12 @@ int m3d_viterbi_filter(const double* cand_dev, int64_t S, int64_t F, int32_t P, 
 /* Number of kernels this library has launched on the calling process (bench.py's
  * gpu_launches). */
 int64_t m3d_launch_count(void);
+/* Per-kernel device times for bench.py's roofline: while enabled, the launches of the triangulation
+ * and subset-search kernels are bracketed by CUDA events on their own stream.  m3d_profile_read
+ * waits for the recorded launches, writes {"kernel": {"launches": n, "ms": total}, ...} (JSON,
+ * NUL-terminated) into buf and clears the records.  Off by default; process-wide. */
+int m3d_profile_enable(int32_t on);
+int m3d_profile_read(char* buf, int64_t cap);
 /* fp64 FMA peak probe: runs a dependent-chain DFMA kernel and returns TFLOP/s. */
 int m3d_probe_fp64_tflops(int32_t device, double* tflops_out);
 

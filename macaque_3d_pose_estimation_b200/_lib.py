@@ -61,6 +61,8 @@ SIGNATURES = {
     "m3d_triangulate_possible": (ctypes.c_int, [_P, _P, _L, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P]),
     "m3d_triangulate_error_host": (ctypes.c_int, [_P, _P, _L, _I, _P, _P]),
     "m3d_triangulate_ransac_host": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
+    "m3d_triangulate_error_host_f32": (ctypes.c_int, [_P, _P, _L, _I, _P, _P]),
+    "m3d_triangulate_ransac_host_f32": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "m3d_host_register": (ctypes.c_int, [_P, _L]),
     "m3d_host_unregister": (ctypes.c_int, [_P]),
     "m3d_ray_affinity": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _D, _P, _P, _P]),
@@ -68,6 +70,8 @@ SIGNATURES = {
     "m3d_match_svt": (ctypes.c_int, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _I, _P, _P, _I, _P]),
     "m3d_viterbi_filter": (ctypes.c_int, [_P, _L, _L, _I, _I, _D, _D, _D, _P, _P, _I, _P]),
     "m3d_launch_count": (_L, []),
+    "m3d_profile_enable": (ctypes.c_int, [_I]),
+    "m3d_profile_read": (ctypes.c_int, [ctypes.c_char_p, _L]),
     "m3d_probe_fp64_tflops": (ctypes.c_int, [_I, ctypes.POINTER(_D)]),
 }
 

@@ -41,6 +41,8 @@ struct m3d_rig {
   double* ws_p3d[kSlots] = {nullptr, nullptr, nullptr};
   double* ws_err[kSlots] = {nullptr, nullptr, nullptr};
   double* ws_xyp[kSlots] = {nullptr, nullptr, nullptr};
+  float* ws_xy32[kSlots] = {nullptr, nullptr, nullptr};   // float32 staging of the *_host_f32 entry points
+  float* ws_xyp32[kSlots] = {nullptr, nullptr, nullptr};
   uint8_t* ws_picked[kSlots] = {nullptr, nullptr, nullptr};
   int32_t* ws_subset[kSlots] = {nullptr, nullptr, nullptr};
   int32_t* ws_neval[kSlots] = {nullptr, nullptr, nullptr};

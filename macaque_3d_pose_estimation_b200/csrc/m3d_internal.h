@@ -16,6 +16,16 @@ cudaMemPool_t m3d_scratch_pool(int device);
 // device-side camera record / device index of a rig handle
 const m3d::RigDev* m3d_rig_dev(const m3d_rig* rig);
 
+// Optional per-kernel timing (m3d_profile_enable): brackets one launch with CUDA events on its own
+// stream; m3d_profile_read() sums the elapsed times per kernel name.  A no-op unless enabled.
+struct M3dKernelTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  const char* name;
+  M3dKernelTimer(const char* name, cudaStream_t st);
+  ~M3dKernelTimer();
+};
+
 struct M3dDeviceGuard {
   int prev = -1;
   bool changed = false;

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -33,6 +34,32 @@ using namespace m3d;
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
+
+// ---- optional per-kernel timing ------------------------------------------------------------
+static std::atomic<bool> g_prof{false};
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+
+M3dKernelTimer::M3dKernelTimer(const char* nm, cudaStream_t s) : st(s), name(nm) {
+  if (!g_prof.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    e0 = e1 = nullptr;
+    return;
+  }
+  cudaEventRecord(e0, st);
+}
+
+M3dKernelTimer::~M3dKernelTimer() {
+  if (!e0) return;
+  cudaEventRecord(e1, st);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof_recs.push_back({name, e0, e1});
+}
 
 int m3d_fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -327,6 +354,53 @@ int m3d_device_count(void) {
 
 int64_t m3d_launch_count(void) { return g_launches.load(); }
 
+int m3d_profile_enable(int32_t on) {
+  g_prof.store(on != 0);
+  return M3D_OK;
+}
+
+int m3d_profile_read(char* buf, int64_t cap) {
+  if (!buf || cap < 3) return fail(M3D_ERR_INVALID, "m3d_profile_read: buffer too small");
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    recs.swap(g_prof_recs);
+  }
+  struct Acc {
+    std::string name;
+    int64_t n = 0;
+    double ms = 0.0;
+  };
+  std::vector<Acc> acc;
+  for (const ProfRec& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      size_t i = 0;
+      for (; i < acc.size(); ++i)
+        if (acc[i].name == r.name) break;
+      if (i == acc.size()) {
+        acc.emplace_back();
+        acc[i].name = r.name;
+      }
+      acc[i].n += 1;
+      acc[i].ms += ms;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  std::string out = "{";
+  for (size_t i = 0; i < acc.size(); ++i) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", i ? ", " : "", acc[i].name.c_str(),
+             (long long)acc[i].n, acc[i].ms);
+    out += tmp;
+  }
+  out += "}";
+  if ((int64_t)out.size() + 1 > cap) return fail(M3D_ERR_INVALID, "m3d_profile_read: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return M3D_OK;
+}
+
 int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig** out) {
   if (!out) return fail(M3D_ERR_INVALID, "m3d_rig_create: out is NULL");
   *out = nullptr;
@@ -368,6 +442,9 @@ static void free_workspace(m3d_rig* rig) {
     cudaFree(rig->ws_p3d[i]);
     cudaFree(rig->ws_err[i]);
     cudaFree(rig->ws_xyp[i]);
+    cudaFree(rig->ws_xy32[i]);
+    cudaFree(rig->ws_xyp32[i]);
+    rig->ws_xy32[i] = rig->ws_xyp32[i] = nullptr;
     cudaFree(rig->ws_picked[i]);
     cudaFree(rig->ws_subset[i]);
     cudaFree(rig->ws_neval[i]);
@@ -496,6 +573,7 @@ static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, i
                               double* p3d, double* err, cudaStream_t st, int sms) {
   const int grid = grid_for(N, 256, sms);
   const int C = rig->dev.n_cams;
+  M3dKernelTimer timer__("k_triangulate", st);
 #define CALLV(F, P, NC, MB)                                                                         \
   do {                                                                                              \
     if (undistort) {                                                                                \
@@ -572,10 +650,12 @@ static int ensure_workspace(m3d_rig* rig, int64_t chunk, bool ransac) {
   for (int i = 0; i < m3d_rig::kSlots; ++i) {
     M3D_CUDA(cudaStreamCreateWithFlags(&rig->ws_stream[i], cudaStreamNonBlocking));
     M3D_CUDA(cudaMalloc(&rig->ws_xy[i], sizeof(double) * 2 * C * chunk));
+    M3D_CUDA(cudaMalloc(&rig->ws_xy32[i], sizeof(float) * 2 * C * chunk));
     M3D_CUDA(cudaMalloc(&rig->ws_p3d[i], sizeof(double) * 3 * chunk));
     M3D_CUDA(cudaMalloc(&rig->ws_err[i], sizeof(double) * chunk));
     if (ransac) {
       M3D_CUDA(cudaMalloc(&rig->ws_xyp[i], sizeof(double) * 2 * C * chunk));
+      M3D_CUDA(cudaMalloc(&rig->ws_xyp32[i], sizeof(float) * 2 * C * chunk));
       M3D_CUDA(cudaMalloc(&rig->ws_picked[i], (size_t)C * chunk));
       M3D_CUDA(cudaMalloc(&rig->ws_subset[i], sizeof(int32_t) * chunk));
       M3D_CUDA(cudaMalloc(&rig->ws_neval[i], sizeof(int32_t) * chunk));
@@ -589,9 +669,24 @@ static int ensure_workspace(m3d_rig* rig, int64_t chunk, bool ransac) {
 
 static const int64_t kHostChunk = 1 << 19;  // joint-instances per pipeline stage
 
-static int host_pipeline(m3d_rig* rig, const double* xy, int64_t N, int undistort, bool ransac,
+// float32 <-> float64 conversion of observation planes (the *_host_f32 entry points)
+__global__ void __launch_bounds__(256) k_widen(const float2* __restrict__ in, double2* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 q = in[i];
+    out[i] = make_double2((double)q.x, (double)q.y);
+  }
+}
+__global__ void __launch_bounds__(256) k_narrow(const double2* __restrict__ in, float2* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 q = in[i];
+    out[i] = make_float2((float)q.x, (float)q.y);
+  }
+}
+
+// xy / xy_picked: float64 host arrays, or (xy32 / xy_picked32) their float32 forms
+static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int64_t N, int undistort, bool ransac,
                          int min_cams, double threshold, double init_best, double* p3d,
-                         uint8_t* picked, double* xy_picked, double* err, int32_t* subset,
+                         uint8_t* picked, double* xy_picked, float* xy_picked32, double* err, int32_t* subset,
                          int32_t* neval) {
   if (N == 0) return M3D_OK;
   DeviceGuard guard(rig->device);
@@ -601,51 +696,80 @@ static int host_pipeline(m3d_rig* rig, const double* xy, int64_t N, int undistor
   int rc = ensure_workspace(rig, chunk, ransac);
   if (rc) return rc;
   const int sms = sm_count_of(rig->device);
-  int64_t done = 0;
-  for (int it = 0; done < N; ++it) {
-    const int slot = it % m3d_rig::kSlots;
-    cudaStream_t st = rig->ws_stream[slot];
-    const int64_t n = (N - done) < chunk ? (N - done) : chunk;
-    // the slot's previous D2H copies must have left its buffers (same stream => ordered)
-    if (C > 0)
-      M3D_CUDA(cudaMemcpy2DAsync(rig->ws_xy[slot], sizeof(double) * 2 * n, xy + 2 * done,
-                                 sizeof(double) * 2 * N, sizeof(double) * 2 * n, C,
-                                 cudaMemcpyHostToDevice, st));
-    if (!ransac) {
-      rc = launch_triangulate(rig, rig->ws_xy[slot], n, undistort, rig->ws_p3d[slot],
-                              err ? rig->ws_err[slot] : nullptr, st, sms);
-      if (rc) return rc;
-    } else {
-      rc = m3d_launch_ransac(rig, rig->ws_xy[slot], n, undistort, min_cams, threshold, init_best,
-                         rig->ws_p3d[slot], picked ? rig->ws_picked[slot] : nullptr,
-                         xy_picked ? rig->ws_xyp[slot] : nullptr, rig->ws_err[slot],
-                         subset ? rig->ws_subset[slot] : nullptr, neval ? rig->ws_neval[slot] : nullptr, st);
-      if (rc) return rc;
+  const bool want_xyp = xy_picked || xy_picked32;
+  cudaError_t ce = cudaSuccess;
+#define PIPE_CUDA(expr)                          \
+  do {                                           \
+    ce = (expr);                                 \
+    if (ce != cudaSuccess) goto pipe_failed;     \
+  } while (0)
+  {
+    int64_t done = 0;
+    for (int it = 0; done < N; ++it) {
+      const int slot = it % m3d_rig::kSlots;
+      cudaStream_t st = rig->ws_stream[slot];
+      const int64_t n = (N - done) < chunk ? (N - done) : chunk;
+      // the slot's previous D2H copies must have left its buffers (same stream => ordered)
+      if (C > 0) {
+        if (xy32) {
+          PIPE_CUDA(cudaMemcpy2DAsync(rig->ws_xy32[slot], sizeof(float) * 2 * n, xy32 + 2 * done,
+                                      sizeof(float) * 2 * N, sizeof(float) * 2 * n, C, cudaMemcpyHostToDevice, st));
+          k_widen<<<grid_for((int64_t)C * n, 256, sms), 256, 0, st>>>(
+              reinterpret_cast<const float2*>(rig->ws_xy32[slot]), reinterpret_cast<double2*>(rig->ws_xy[slot]),
+              (int64_t)C * n);
+          rc = check_launch("k_widen");
+          if (rc) goto pipe_failed;
+        } else {
+          PIPE_CUDA(cudaMemcpy2DAsync(rig->ws_xy[slot], sizeof(double) * 2 * n, xy + 2 * done,
+                                      sizeof(double) * 2 * N, sizeof(double) * 2 * n, C, cudaMemcpyHostToDevice, st));
+        }
+      }
+      if (!ransac) {
+        rc = launch_triangulate(rig, rig->ws_xy[slot], n, undistort, rig->ws_p3d[slot],
+                                err ? rig->ws_err[slot] : nullptr, st, sms);
+      } else {
+        rc = m3d_launch_ransac(rig, rig->ws_xy[slot], n, undistort, min_cams, threshold, init_best,
+                               rig->ws_p3d[slot], picked ? rig->ws_picked[slot] : nullptr,
+                               want_xyp ? rig->ws_xyp[slot] : nullptr, rig->ws_err[slot],
+                               subset ? rig->ws_subset[slot] : nullptr, neval ? rig->ws_neval[slot] : nullptr, st);
+      }
+      if (rc) goto pipe_failed;
+      PIPE_CUDA(cudaMemcpyAsync(p3d + 3 * done, rig->ws_p3d[slot], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+      if (err)
+        PIPE_CUDA(cudaMemcpyAsync(err + done, rig->ws_err[slot], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+      if (ransac) {
+        if (picked && C > 0)
+          PIPE_CUDA(cudaMemcpy2DAsync(picked + done, (size_t)N, rig->ws_picked[slot], (size_t)n, (size_t)n, C,
+                                      cudaMemcpyDeviceToHost, st));
+        if (xy_picked && C > 0)
+          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked + 2 * done, sizeof(double) * 2 * N, rig->ws_xyp[slot],
+                                      sizeof(double) * 2 * n, sizeof(double) * 2 * n, C, cudaMemcpyDeviceToHost, st));
+        if (xy_picked32 && C > 0) {
+          k_narrow<<<grid_for((int64_t)C * n, 256, sms), 256, 0, st>>>(
+              reinterpret_cast<const double2*>(rig->ws_xyp[slot]), reinterpret_cast<float2*>(rig->ws_xyp32[slot]),
+              (int64_t)C * n);
+          rc = check_launch("k_narrow");
+          if (rc) goto pipe_failed;
+          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked32 + 2 * done, sizeof(float) * 2 * N, rig->ws_xyp32[slot],
+                                      sizeof(float) * 2 * n, sizeof(float) * 2 * n, C, cudaMemcpyDeviceToHost, st));
+        }
+        if (subset)
+          PIPE_CUDA(cudaMemcpyAsync(subset + done, rig->ws_subset[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        if (neval)
+          PIPE_CUDA(cudaMemcpyAsync(neval + done, rig->ws_neval[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+      }
+      done += n;
     }
-    M3D_CUDA(cudaMemcpyAsync(p3d + 3 * done, rig->ws_p3d[slot], sizeof(double) * 3 * n,
-                             cudaMemcpyDeviceToHost, st));
-    if (err)
-      M3D_CUDA(cudaMemcpyAsync(err + done, rig->ws_err[slot], sizeof(double) * n,
-                               cudaMemcpyDeviceToHost, st));
-    if (ransac) {
-      if (picked && C > 0)
-        M3D_CUDA(cudaMemcpy2DAsync(picked + done, (size_t)N, rig->ws_picked[slot], (size_t)n, (size_t)n,
-                                   C, cudaMemcpyDeviceToHost, st));
-      if (xy_picked && C > 0)
-        M3D_CUDA(cudaMemcpy2DAsync(xy_picked + 2 * done, sizeof(double) * 2 * N, rig->ws_xyp[slot],
-                                   sizeof(double) * 2 * n, sizeof(double) * 2 * n, C,
-                                   cudaMemcpyDeviceToHost, st));
-      if (subset)
-        M3D_CUDA(cudaMemcpyAsync(subset + done, rig->ws_subset[slot], sizeof(int32_t) * n,
-                                 cudaMemcpyDeviceToHost, st));
-      if (neval)
-        M3D_CUDA(cudaMemcpyAsync(neval + done, rig->ws_neval[slot], sizeof(int32_t) * n,
-                                 cudaMemcpyDeviceToHost, st));
-    }
-    done += n;
   }
-  for (int i = 0; i < m3d_rig::kSlots; ++i) M3D_CUDA(cudaStreamSynchronize(rig->ws_stream[i]));
+  for (int i = 0; i < m3d_rig::kSlots; ++i) PIPE_CUDA(cudaStreamSynchronize(rig->ws_stream[i]));
   return M3D_OK;
+pipe_failed:
+  // earlier chunks may still be copying into the caller's buffers: drain every slot before the
+  // caller is told (and frees them)
+  for (int i = 0; i < m3d_rig::kSlots; ++i) cudaStreamSynchronize(rig->ws_stream[i]);
+#undef PIPE_CUDA
+  if (rc) return rc;
+  return fail(M3D_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(ce));
 }
 
 int m3d_triangulate_error_host(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
@@ -654,8 +778,18 @@ int m3d_triangulate_error_host(const m3d_rig* rig, const double* xy, int64_t N, 
   if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host: negative point count");
   if (N > 0 && (!p3d || (!xy && rig->dev.n_cams > 0)))
     return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host: NULL buffer");
-  return host_pipeline(const_cast<m3d_rig*>(rig), xy, N, undistort, false, 0, 0, 0, p3d, nullptr,
-                       nullptr, err, nullptr, nullptr);
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, nullptr, N, undistort, false, 0, 0, 0, p3d, nullptr,
+                       nullptr, nullptr, err, nullptr, nullptr);
+}
+
+int m3d_triangulate_error_host_f32(const m3d_rig* rig, const float* xy, int64_t N, int32_t undistort,
+                                   double* p3d, double* err) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_f32: rig is NULL");
+  if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_f32: negative point count");
+  if (N > 0 && (!p3d || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_f32: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), nullptr, xy, N, undistort, false, 0, 0, 0, p3d, nullptr,
+                       nullptr, nullptr, err, nullptr, nullptr);
 }
 
 int m3d_triangulate_ransac_host(const m3d_rig* rig, const double* xy, int64_t N, int32_t undistort,
@@ -666,8 +800,20 @@ int m3d_triangulate_ransac_host(const m3d_rig* rig, const double* xy, int64_t N,
   if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host: negative point count");
   if (N > 0 && (!p3d || !err || (!xy && rig->dev.n_cams > 0)))
     return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host: NULL buffer");
-  return host_pipeline(const_cast<m3d_rig*>(rig), xy, N, undistort, true, min_cams, threshold,
-                       init_best, p3d, picked, xy_picked, err, subset, neval);
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, nullptr, N, undistort, true, min_cams, threshold,
+                       init_best, p3d, picked, xy_picked, nullptr, err, subset, neval);
+}
+
+int m3d_triangulate_ransac_host_f32(const m3d_rig* rig, const float* xy, int64_t N, int32_t undistort,
+                                    int32_t min_cams, double threshold, double init_best, double* p3d,
+                                    uint8_t* picked, float* xy_picked, double* err, int32_t* subset,
+                                    int32_t* neval) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_f32: rig is NULL");
+  if (N < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_f32: negative point count");
+  if (N > 0 && (!p3d || !err || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_f32: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), nullptr, xy, N, undistort, true, min_cams, threshold,
+                       init_best, p3d, picked, nullptr, xy_picked, err, subset, neval);
 }
 
 int m3d_host_register(void* ptr, int64_t bytes) {

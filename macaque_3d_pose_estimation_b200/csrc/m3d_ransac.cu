@@ -94,12 +94,13 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
     const int64_t cap = (int64_t)sms * 3 * 32;
     if (blocksA > cap) blocksA = cap;
 #define CALLA(PO, NC)                                                                                        \
+  M3dKernelTimer timer__("k_cert_setup", st);                                                                \
   k_cert_setup<PO, NC><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,       \
                                                           min_cams, threshold, init_best, slots, rec, counters)
     if (C == 8) {
-      if (po) CALLA(true, 8); else CALLA(false, 8);
+      if (po) { CALLA(true, 8); } else { CALLA(false, 8); }
     } else {
-      if (po) CALLA(true, 0); else CALLA(false, 0);
+      if (po) { CALLA(true, 0); } else { CALLA(false, 0); }
     }
 #undef CALLA
     rc = check_launch("k_cert_setup");
@@ -107,6 +108,7 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
 #define CALLB(PO, NC, MB)                                                                                    \
   do {                                                                                                       \
     auto kfn = k_cert_search<PO, NC, MB>;                                                                    \
+    M3dKernelTimer timer__("k_cert_search", st);                                                             \
     int per_sm = 0;                                                                                          \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, 0);                                     \
     if (per_sm < 1) per_sm = 1;                                                                              \
@@ -125,8 +127,11 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
 #undef CALLB
     rc = check_launch("k_cert_search");
     if (rc) return rc;
-    k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
-                                                         subset, neval);
+    {
+      M3dKernelTimer timer__("k_ransac_emit", st);
+      k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
+                                                           subset, neval);
+    }
     rc = check_launch("k_ransac_emit");
     if (rc) return rc;
   }

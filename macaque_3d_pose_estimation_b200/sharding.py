@@ -1,9 +1,17 @@
-"""Frame-chunk sharding of the hot path over the GPUs of one box.
+"""Frame sharding of the hot path over the GPUs of one box.
 
-Every joint-instance is independent, so ranks own contiguous frame ranges and never
-exchange data while computing; the only collective is the final gather of the 3D results
-(p3d + err = 32 B per joint-instance; ``picked`` optionally) to one rank.  Works with any
-``torch.distributed`` backend (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+Every joint-instance is independent, so ranks never exchange data while computing.  The recording
+is cut into TILES of ``tile_frames`` consecutive frames that are dealt round-robin (tile t belongs
+to rank t % world): the per-point cost of the subset RANSAC is heavy-tailed and clusters in time
+(occlusions), so interleaving balances the ranks, and one ROUND (one tile of every rank) is a
+contiguous block of ``world`` tiles of the recording.
+
+The only collective is the gather of the 3D results (p3d + err = 32 B per joint-instance) to one
+rank.  It is issued PER ROUND, asynchronously (``async_op=True``: NCCL's own stream), straight into
+the destination's frame-ordered result arrays (round j lands at rows [j * world * tile, ...) — no
+reorder pass), while the next round's kernels run; the step ends when the last gather has landed.
+Works with any ``torch.distributed`` backend (NCCL over NVLink on the B200 box, gloo in the CPU
+tests).  A rank only ever holds the observations of its own tiles.
 """
 import numpy as np
 
@@ -14,10 +22,45 @@ except Exception:  # pragma: no cover
     torch = None
     dist = None
 
+RANSAC_TILE_FRAMES = 256
+
+
+class TilePlan:
+    """Round-robin deal of tiles of ``tile_frames`` frames (``per`` joint-instances per frame)."""
+
+    def __init__(self, n_frames, world, tile_frames, per):
+        self.n_frames = int(n_frames)
+        self.world = int(world)
+        self.per = int(per)
+        # a tile never needs to be larger than an even split: keeps every rank busy on short clips
+        even = -(-self.n_frames // self.world) if self.n_frames else 1
+        self.tile = max(1, min(int(tile_frames), even))
+        self.n_tiles = -(-self.n_frames // self.tile) if self.n_frames else 0
+        self.rounds = -(-self.n_tiles // self.world) if self.n_tiles else 0
+
+    def tile_span(self, t):
+        """Frame range [lo, hi) of tile t (empty when t is past the end)."""
+        lo = min(t * self.tile, self.n_frames)
+        return lo, min(lo + self.tile, self.n_frames)
+
+    def frames_of(self, rank):
+        """Frames of ``rank`` in the order it processes them."""
+        spans = [self.tile_span(j * self.world + rank) for j in range(self.rounds)]
+        parts = [np.arange(a, b, dtype=np.int64) for a, b in spans if b > a]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+    def local_offset(self, rank, j):
+        """Row offset (joint-instances) of round j inside rank's local arrays."""
+        done = 0
+        for i in range(j):
+            a, b = self.tile_span(i * self.world + rank)
+            done += b - a
+        return done * self.per
+
 
 def frame_range(n_frames, rank, world_size):
     """Contiguous, balanced frame range [lo, hi) of ``rank`` (first n_frames % world ranks get
-    one extra frame)."""
+    one extra frame) — the layout of the DLT path, which has uniform cost per point."""
     base, rem = divmod(int(n_frames), int(world_size))
     lo = rank * base + min(rank, rem)
     hi = lo + base + (1 if rank < rem else 0)
@@ -25,97 +68,156 @@ def frame_range(n_frames, rank, world_size):
 
 
 def tile_frames_of(n_frames, rank, world_size, tile):
-    """Frames of ``rank`` when tiles of ``tile`` consecutive frames are dealt round-robin
-    (tile t belongs to rank t % world_size): the layout for the subset RANSAC, whose per-point
-    cost is heavy-tailed and clusters in time (occlusions), SURVEY.md §8e."""
-    tile = max(1, int(tile))
-    starts = np.arange(rank * tile, int(n_frames), tile * int(world_size))
-    if starts.size == 0:
-        return np.zeros(0, dtype=np.int64)
-    return np.concatenate([np.arange(a, min(a + tile, int(n_frames))) for a in starts]).astype(np.int64)
-
-
-def _frames_of(n_frames, rank, world_size, tile):
-    if tile is None:
-        lo, hi = frame_range(n_frames, rank, world_size)
-        return np.arange(lo, hi, dtype=np.int64)
-    return tile_frames_of(n_frames, rank, world_size, tile)
+    """Frames of ``rank`` under the round-robin deal of tiles of ``tile`` frames."""
+    return TilePlan(n_frames, world_size, tile, 1).frames_of(rank)
 
 
 def shard_points(points, n_frames, rank, world_size, tile=None):
-    """Slice the (C, F*P, 2) observation array (frame-major point order) to this rank's frames:
-    one contiguous range (``tile`` None) or round-robin tiles of ``tile`` frames."""
+    """Slice a (C, F*per, 2) observation array (frame-major point order) to this rank's frames:
+    one contiguous range (``tile`` None) or round-robin tiles of ``tile`` frames.  Convenience for
+    callers that hold the whole recording; the sharded run itself only needs the local slice."""
     n = points.shape[1]
-    assert n % n_frames == 0, "point count is not a multiple of the frame count"
-    per = n // n_frames
+    assert n_frames == 0 or n % n_frames == 0, "point count is not a multiple of the frame count"
+    per = n // n_frames if n_frames else 0
     if tile is None:
         lo, hi = frame_range(n_frames, rank, world_size)
         return points[:, lo * per:hi * per]
-    fr = tile_frames_of(n_frames, rank, world_size, tile)
+    fr = TilePlan(n_frames, world_size, tile, per).frames_of(rank)
     idx = (fr[:, None] * per + np.arange(per)[None, :]).reshape(-1)
     if torch is not None and isinstance(points, torch.Tensor):
         return points[:, torch.as_tensor(idx, device=points.device)]
     return points[:, idx]
 
 
-def gather_results(tensors, n_frames, dst=0, group=None, tile=None):
-    """Gather per-rank result tensors (first dim = this rank's joint-instances, frame-major)
-    to ``dst`` in global frame order.  Returns the concatenated tensors on ``dst`` and None
-    elsewhere.  Uneven shards are handled by padding to the largest shard; round-robin tiles
-    (``tile``) are put back into frame order on ``dst``."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    frames = [_frames_of(n_frames, r, world, tile) for r in range(world)]
-    outs = []
-    for t in tensors:
-        per = t.shape[0] // max(1, frames[rank].size)
-        sizes = [f.size * per for f in frames]
-        mx = max(sizes)
-        pad = t
-        if t.shape[0] < mx:
-            pad = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))])
-        pad = pad.contiguous()
-        if rank == dst:
-            bufs = [torch.empty_like(pad) for _ in range(world)]
-            dist.gather(pad, bufs, dst=dst, group=group)
-            res = torch.cat([b[:s] for b, s in zip(bufs, sizes)])
-            if tile is not None:
-                order = np.argsort(np.concatenate(frames), kind="stable")          # rank-major -> frame order
-                idx = (order[:, None] * per + np.arange(per)[None, :]).reshape(-1)
-                res = res[torch.as_tensor(idx, device=res.device)]
-            outs.append(res)
-        else:
-            dist.gather(pad, None, dst=dst, group=group)
-            outs.append(None)
-    return outs
+class RoundGather:
+    """The per-round gather of result rows to ``dst`` in global frame order.
+
+    ``add(j, tensors)`` is called by every rank after it has queued the kernels of round j;
+    ``tensors`` are this rank's result arrays of that round (rows = joint-instances of its tile,
+    possibly fewer than a full tile, possibly none).  ``finish()`` waits for all gathers and
+    returns the global arrays on ``dst`` (None elsewhere)."""
+
+    def __init__(self, plan, row_shapes, dtype, device, dst=0, group=None):
+        self.plan = plan
+        self.group = group
+        self.dst = dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.tile_rows = plan.tile * plan.per
+        self.works = []
+        self.fixups = []
+        self.out = None
+        self.device = device
+        self.dtype = dtype
+        self.row_shapes = [tuple(s) for s in row_shapes]
+        if self.rank == dst:
+            total = plan.n_frames * plan.per
+            self.out = [torch.empty((total,) + s, dtype=dtype, device=device) for s in self.row_shapes]
+        # staging for a short / missing tile: every rank contributes exactly tile_rows rows
+        self._pad = None
+
+    def _padded(self, t, shape):
+        if t is not None and t.shape[0] == self.tile_rows:
+            return t.contiguous()
+        buf = torch.zeros((self.tile_rows,) + shape, dtype=self.dtype, device=self.device)
+        if t is not None and t.shape[0] > 0:
+            buf[:t.shape[0]].copy_(t)
+        return buf
+
+    def add(self, j, tensors):
+        plan = self.plan
+        for k, shape in enumerate(self.row_shapes):
+            send = self._padded(tensors[k] if tensors is not None else None, shape)
+            if self.rank == self.dst:
+                bufs = []
+                for r in range(self.world):
+                    a, b = plan.tile_span(j * self.world + r)
+                    rows = (b - a) * plan.per
+                    if rows == self.tile_rows:      # full tile: receive in place, already in frame order
+                        bufs.append(self.out[k][a * plan.per:b * plan.per])
+                    else:                           # ragged end of the recording
+                        tmp = torch.empty((self.tile_rows,) + shape, dtype=self.dtype, device=self.device)
+                        bufs.append(tmp)
+                        if rows > 0:
+                            self.fixups.append((k, a * plan.per, rows, tmp))
+                self.works.append(dist.gather(send, bufs, dst=self.dst, group=self.group, async_op=True))
+            else:
+                self.works.append(dist.gather(send, None, dst=self.dst, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        for k, off, rows, tmp in self.fixups:
+            self.out[k][off:off + rows].copy_(tmp[:rows])
+        self.fixups = []
+        return self.out
 
 
-RANSAC_TILE_FRAMES = 256
-
-
-def triangulate_sharded(cgroup, points, n_frames, ransac=False, min_cams=2, gather=True, group=None,
+def triangulate_sharded(cgroup, local_points, n_frames, ransac=False, min_cams=2, gather=True, group=None,
                         tile_frames="auto"):
-    """Run this rank's frames of ``points`` (C, F*P, 2, the full array on every rank) through the
-    GPU CameraGroup and gather (p3d, err) to rank 0.  Returns (p3d, err) on rank 0 in global
-    frame order (or the local shard when ``gather`` is False).  ``tile_frames``: None = one
-    contiguous frame range per rank; an int = round-robin tiles of that many frames; "auto" =
-    contiguous for the DLT path, tiles of RANSAC_TILE_FRAMES for the subset RANSAC."""
+    """Run this rank's frames through the GPU CameraGroup and gather (p3d, err) to rank 0.
+
+    ``local_points`` (C, n_local, 2): the observations of THIS rank's frames only, in the order of
+    ``TilePlan(...).frames_of(rank)`` (``shard_points`` cuts them out of a full recording);
+    ``n_frames``: frames of the whole recording.  ``tile_frames``: an int = tile size of the
+    round-robin deal; "auto" = about 16 tiles per rank (at least RANSAC_TILE_FRAMES frames each) for the
+    subset RANSAC and one even split per rank for the DLT path.  Returns (p3d, err) of the whole recording in frame order on rank 0, (None,
+    None) on the other ranks; with ``gather=False`` every rank gets its local results."""
     world = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    tile = (RANSAC_TILE_FRAMES if ransac else None) if tile_frames == "auto" else tile_frames
-    if world == 1:
-        tile = None
-    local = shard_points(points, n_frames, rank, world, tile)
-    if ransac:
-        p3d, _, _, err = cgroup.triangulate_ransac(local, min_cams=min_cams)
+    per_guess = 0
+    if tile_frames == "auto" or tile_frames is None:
+        even = max(1, -(-int(n_frames) // world))
+        # RANSAC: interleave, but keep a step at ~16 rounds (a launch + a gather per round)
+        tile = max(RANSAC_TILE_FRAMES, -(-even // 16)) if ransac else even
     else:
-        p3d, err = cgroup.triangulate_with_error(local)
-    if world == 1 or not gather:
+        tile = int(tile_frames)
+    # joint-instances per frame from GLOBAL data: a rank may own no frame at all
+    plan0 = TilePlan(n_frames, world, tile, 1)
+    mine = plan0.frames_of(rank).size
+    n_local = local_points.shape[1]
+    if world > 1:
+        t = torch.tensor([n_local, mine], dtype=torch.int64)
+        dev = None
+        if dist.get_backend(group) == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = t.to(dev)
+        dist.all_reduce(t, group=group)
+        tot_points, tot_frames = int(t[0]), int(t[1])
+    else:
+        tot_points, tot_frames = n_local, mine
+    assert tot_frames == int(n_frames), "tile plan does not cover the recording"
+    per_guess = tot_points // int(n_frames) if n_frames else 0
+    assert per_guess * int(n_frames) == tot_points and n_local == mine * per_guess, \
+        "local point count does not match this rank's frames"
+    plan = TilePlan(n_frames, world, tile, per_guess)
+
+    def run(pts):
+        if ransac:
+            p3d, _, _, err = cgroup.triangulate_ransac(pts, min_cams=min_cams)
+        else:
+            p3d, err = cgroup.triangulate_with_error(pts)
         return p3d, err
-    as_t = [torch.as_tensor(p3d), torch.as_tensor(err)]
-    g = gather_results(as_t, n_frames, dst=0, group=group, tile=tile)
+
+    if world == 1 or not gather:
+        return run(local_points)
+
+    as_numpy = isinstance(local_points, np.ndarray)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    rg = RoundGather(plan, [(3,), ()], torch.float64, device, dst=0, group=group)
+    for j in range(plan.rounds):
+        a, b = plan.tile_span(j * world + rank)
+        res = None
+        if b > a:
+            off = plan.local_offset(rank, j)
+            p3d, err = run(local_points[:, off:off + (b - a) * plan.per])
+            res = [torch.as_tensor(p3d).to(device), torch.as_tensor(err).to(device)]
+        rg.add(j, res)
+    out = rg.finish()
     if rank != 0:
         return None, None
-    if isinstance(p3d, np.ndarray):
-        return g[0].cpu().numpy(), g[1].cpu().numpy()
-    return g[0], g[1]
+    if as_numpy:
+        return out[0].cpu().numpy(), out[1].cpu().numpy()
+    return out[0], out[1]

@@ -47,7 +47,13 @@ def _worker(rank, world, port, n_frames, ransac, tmp, tile="auto"):
         cg = OracleGroup(dicts)
         X = synth.make_tracks(n_frames, 2, n_joints=5, seed=31).reshape(-1, 3)
         p2 = synth.corrupt(og.project(cg.cameras, X), seed=31, p_outlier=0.2 if ransac else 0.0, p_missing=0.1)
-        p3d, err = sharding.triangulate_sharded(cg, p2, n_frames, ransac=ransac, tile_frames=tile)
+        # every rank is handed the observations of its own frames only
+        tl = tile
+        if tl == "auto":
+            even = max(1, -(-n_frames // world))
+            tl = max(sharding.RANSAC_TILE_FRAMES, -(-even // 16)) if ransac else even
+        local = sharding.shard_points(p2, n_frames, rank, world, tl)
+        p3d, err = sharding.triangulate_sharded(cg, local, n_frames, ransac=ransac, tile_frames=tile)
         if rank == 0:
             np.savez(tmp, p3d=p3d, err=err, p2=p2)
         else:
@@ -56,7 +62,8 @@ def _worker(rank, world, port, n_frames, ransac, tmp, tile="auto"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,ransac,tile", [(11, False, "auto"), (6, True, "auto"), (7, True, 2), (9, False, 1)])
+@pytest.mark.parametrize("n_frames,ransac,tile", [(11, False, "auto"), (6, True, "auto"), (7, True, 2), (9, False, 1),
+                                                  (1, True, 256), (5, True, 3), (0, False, "auto")])
 def test_sharded_matches_single_process(tmp_path, n_frames, ransac, tile):
     tmp = str(tmp_path / "out.npz")
     mp.spawn(_worker, args=(2, _free_port(), n_frames, ransac, tmp, tile), nprocs=2, join=True)
@@ -76,6 +83,12 @@ def test_round_robin_tiles_partition():
             for t in (1, 3, 256):
                 fr = [sharding.tile_frames_of(n, r, w, t) for r in range(w)]
                 assert np.array_equal(np.sort(np.concatenate(fr)), np.arange(n))
+                plan = sharding.TilePlan(n, w, t, 3)
+                # a round is a contiguous block of the recording; a short clip still feeds every rank
+                assert plan.tile <= max(1, -(-n // w))
+                for r in range(w):
+                    offs = [plan.local_offset(r, j) for j in range(plan.rounds + 1)]
+                    assert offs[-1] == 3 * fr[r].size
                 assert all((f[1:] > f[:-1]).all() for f in fr if f.size > 1)
 
 
