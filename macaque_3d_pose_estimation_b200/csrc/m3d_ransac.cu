@@ -33,7 +33,7 @@ static const int64_t kRansacChunk = 1 << 22;
 // scratch of one ransac launch, returned to the rig's pool on every exit path
 struct PoolScratch {
   cudaStream_t st;
-  void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n = 0;
   explicit PoolScratch(cudaStream_t s) : st(s) {}
   cudaError_t alloc(void** out, size_t bytes, cudaMemPool_t pool) {
@@ -80,27 +80,39 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
   PoolScratch scratch(st);
   RansacSlot* slots = nullptr;
   double2* rec = nullptr;
-  unsigned int* counters = nullptr;  // [0] records queued, [1] records taken
+  unsigned int* counters = nullptr;  // [0] records queued, [1] records taken, [2] parked, [3] parked taken
+  unsigned int* over = nullptr;      // queue indices of the parked searches
   M3D_CUDA(scratch.alloc((void**)&slots, sizeof(RansacSlot) * (size_t)chunk, rig->pool));
   M3D_CUDA(scratch.alloc((void**)&rec, rec_bytes, rig->pool));
-  M3D_CUDA(scratch.alloc((void**)&counters, 2 * sizeof(unsigned int), rig->pool));
+  M3D_CUDA(scratch.alloc((void**)&counters, 4 * sizeof(unsigned int), rig->pool));
+  M3D_CUDA(scratch.alloc((void**)&over, sizeof(unsigned int) * (size_t)chunk, rig->pool));
   const bool po = (rig->dev.flags & RIG_HAS_NONPINHOLE) == 0;
   // developer switch: CTAs per SM of the persistent search kernel (2 = 255 registers, 3 = 168)
+  static const int setup_ctas = [] { const char* e = getenv("M3D_CERT_SETUP_CTAS"); return e ? atoi(e) : 0; }();
   static const int search_ctas = [] { const char* e = getenv("M3D_CERT_CTAS"); return e ? atoi(e) : 0; }();
+  // evaluations a lane of k_cert_search spends on one point before it parks the search for
+  // k_cert_overflow (developer switch M3D_CERT_LANE_LIMIT; 0 = never park)
+  static const int lane_limit = [] {
+    const char* e = getenv("M3D_CERT_LANE_LIMIT");
+    const int v = e ? atoi(e) : 32;
+    return v > 0 ? v : 0x7fffffff;
+  }();
   for (int64_t n0 = 0; n0 < N; n0 += chunk) {
     const int64_t n = (N - n0) < chunk ? (N - n0) : chunk;
-    M3D_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st));
+    M3D_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), st));
     int64_t blocksA = (n + 127) / 128;
     const int64_t cap = (int64_t)sms * 3 * 32;
     if (blocksA > cap) blocksA = cap;
-#define CALLA(PO, NC)                                                                                        \
+#define CALLA(PO, NC, MB)                                                                                    \
   M3dKernelTimer timer__("k_cert_setup", st);                                                                \
-  k_cert_setup<PO, NC><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,       \
-                                                          min_cams, threshold, init_best, slots, rec, counters)
+  k_cert_setup<PO, NC, MB><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,   \
+                                                              min_cams, threshold, init_best, slots, rec, counters)
     if (C == 8) {
-      if (po) { CALLA(true, 8); } else { CALLA(false, 8); }
+      if (setup_ctas == 4) { if (po) { CALLA(true, 8, 4); } else { CALLA(false, 8, 4); } }
+      else if (setup_ctas == 2) { if (po) { CALLA(true, 8, 2); } else { CALLA(false, 8, 2); } }
+      else { if (po) { CALLA(true, 8, 3); } else { CALLA(false, 8, 3); } }
     } else {
-      if (po) { CALLA(true, 0); } else { CALLA(false, 0); }
+      if (po) { CALLA(true, 0, 2); } else { CALLA(false, 0, 2); }
     }
 #undef CALLA
     rc = check_launch("k_cert_setup");
@@ -116,16 +128,32 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
     const int64_t need = (n + 127) / 128;                                                                    \
     if (blocks > need) blocks = need;                                                                        \
     kfn<<<(unsigned)blocks, 128, 0, st>>>(rig->dev, rig->cumb_g, min_cams, threshold, init_best, slots, rec, \
-                                          counters, counters + 1);                                           \
+                                          counters, counters + 1, over, counters + 2, lane_limit);           \
   } while (0)
     if (C == 8) {
       if (search_ctas == 2) { if (po) CALLB(true, 8, 2); else CALLB(false, 8, 2); }
+      else if (search_ctas == 4) { if (po) CALLB(true, 8, 4); else CALLB(false, 8, 4); }
       else { if (po) CALLB(true, 8, 3); else CALLB(false, 8, 3); }
     } else {
       if (po) CALLB(true, 0, 2); else CALLB(false, 0, 2);
     }
 #undef CALLB
     rc = check_launch("k_cert_search");
+    if (rc) return rc;
+    {
+      M3dKernelTimer timer__("k_cert_overflow", st);
+      const unsigned ob = (unsigned)(sms * 2);
+#define CALLO(PO, NC)                                                                                        \
+  k_cert_overflow<PO, NC><<<ob, 128, 0, st>>>(rig->dev, rig->cumb_g, min_cams, threshold, init_best, slots, rec, \
+                                              over, counters + 2, counters + 3)
+      if (C == 8) {
+        if (po) CALLO(true, 8); else CALLO(false, 8);
+      } else {
+        if (po) CALLO(true, 0); else CALLO(false, 0);
+      }
+#undef CALLO
+    }
+    rc = check_launch("k_cert_overflow");
     if (rc) return rc;
     {
       M3dKernelTimer timer__("k_ransac_emit", st);

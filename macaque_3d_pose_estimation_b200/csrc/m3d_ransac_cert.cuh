@@ -314,6 +314,9 @@ M3D_HD void ransac_cert_point(const RigDev& rig, const CertDev& cert, const uint
 //   k_cert_search  persistent lanes: every lane owns one queued point and evaluates one
 //                  surviving subset per trip; a lane that finishes takes the next record at once,
 //                  so all 32 lanes evaluate on (almost) every trip
+//   k_cert_overflow  the few searches that outlast `lane_limit` evaluations in a lane (points
+//                  without a clean subset: up to 2^k evaluations) are parked by k_cert_search and
+//                  finished here warp-cooperatively, 32 surviving subsets per round
 //   k_ransac_emit  (m3d_ransac.cuh) expands the slots into the reference's outputs
 // Record q: fields of 16 bytes, field f of record q at ((q / 32) * F + f) * 32 + q % 32 (so that 32
 // consecutive records are read / written with full sectors):
@@ -323,8 +326,8 @@ M3D_HD void ransac_cert_point(const RigDev& rig, const CertDev& cert, const uint
 // ---------------------------------------------------------------------------------------
 M3D_HD int cert_record_fields(int C) { return 2 * C + 3 + (C + 7) / 8; }
 
-template <bool PO, int NC>
-__global__ void __launch_bounds__(128, NC == 8 ? 3 : 2)
+template <bool PO, int NC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_cert_setup(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev cert,
              const double* __restrict__ xy, int64_t ld, int64_t n0, int64_t n, int undistort, int min_cams,
              double thr, double init_best, RansacSlot* __restrict__ slots, double2* __restrict__ rec,
@@ -420,8 +423,9 @@ k_cert_setup(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev
 template <bool PO, int NC, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ cumb, int min_cams, double thr,
-              double init_best, RansacSlot* __restrict__ slots, const double2* __restrict__ rec,
-              const unsigned int* __restrict__ n_rec, unsigned int* __restrict__ counter) {
+              double init_best, RansacSlot* __restrict__ slots, double2* __restrict__ rec,
+              const unsigned int* __restrict__ n_rec, unsigned int* __restrict__ counter,
+              unsigned int* __restrict__ over, unsigned int* __restrict__ n_over, int lane_limit) {
   constexpr int CC = NC > 0 ? NC : M3D_MAXC;
   constexpr unsigned FULLM = 0xffffffffu;
   const int C = NC > 0 ? NC : rig.n_cams;
@@ -431,8 +435,8 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
   const unsigned int total = *n_rec;
   XY raw[CC], xh[CC];
   uint32_t badrow[CC];
-  uint32_t v = 0, u = 0, d = 0, best_d = 0, idx = 0;
-  int pass = 1;
+  uint32_t v = 0, u = 0, d = 0, best_d = 0, idx = 0, qrec = 0;
+  int pass = 1, n_done = 0;
   bool active = false, drained = false, have = false;
   double best_err = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
 #pragma unroll 1
@@ -478,13 +482,9 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
           best_d = 0;
           pass = 1;
           active = true;
-          d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
-          if (d == 0 && T1 < best_err) {  // every subset is certified-bad: arg-min scan
-            pass = 2;
-#pragma unroll
-            for (int p = 0; p < CC; ++p) badrow[p] = 0;
-            d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
-          }
+          qrec = q;
+          n_done = 0;
+          d = 0;
         } else {
           drained = true;
         }
@@ -492,13 +492,34 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
     }
     if (!__any_sync(FULLM, active)) break;
     if (active) {
+      // ---- every lane moves to its next surviving subset (one convergent pass per trip)
       bool stop = false, ran_out = false;
+      d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
+      if (d == 0 && pass == 1 && T1 < best_err) {
+        // nothing under T1: rescan everything for the strict arg-min, without pruning
+        pass = 2;
+#pragma unroll
+        for (int p = 0; p < CC; ++p) badrow[p] = 0;
+        d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+      }
       if (d == 0) {
-        stop = ran_out = true;  // no candidate at all
+        stop = ran_out = true;
+      } else if (n_done >= lane_limit) {
+        // a long search (a point without a clean subset, a point far outside the images) would
+        // keep this lane — in the end this whole warp — busy for hundreds of trips: park its
+        // state in the record and hand it to the warp-cooperative kernel
+        double2* r = rec + ((size_t)(qrec >> 5) * F) * 32 + (qrec & 31u);
+        reinterpret_cast<uint4*>(r)[(size_t)(2 * C) * 32] =
+            make_uint4(v | (u << 16), idx, d, (uint32_t)pass | (have ? 256u : 0u) | (best_d << 16));
+        r[(size_t)(2 * C + 1) * 32] = make_double2(best_err, bx);
+        r[(size_t)(2 * C + 2) * 32] = make_double2(by, bz);
+        over[atomicAdd(n_over, 1u)] = qrec;
+        active = false;
       } else {
         const uint32_t kept = v & ~d;
         double X, Y, Z;
         const double err = cert_eval<PO, NC>(rig, raw, xh, kept, kept & u, X, Y, Z);
+        ++n_done;
         if (pass == 1) {
           if (err < T1) {
             best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
@@ -506,16 +527,6 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
           }
         } else if (err < best_err) {
           best_err = err, best_d = d, have = true, bx = X, by = Y, bz = Z;
-        }
-        if (!stop) {
-          d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
-          if (d == 0 && pass == 1 && T1 < best_err) {
-            pass = 2;
-#pragma unroll
-            for (int p = 0; p < CC; ++p) badrow[p] = 0;
-            d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
-          }
-          if (d == 0) stop = ran_out = true;
         }
       }
       if (stop) {
@@ -533,6 +544,154 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
         sl->neval = ne;
         active = false;
       }
+    }
+  }
+}
+
+// Warp-cooperative continuation of the searches k_cert_search parked: one warp = one point, lane j
+// takes the j-th surviving subset after the current one (the subsets of a round are evaluated at
+// once); pass 1 stops at the first lane (= first subset in enumeration order) under T1, pass 2
+// reduces the strict arg-min (first on ties) over all lanes at the end.
+template <bool PO, int NC>
+__global__ void __launch_bounds__(128, 2)
+k_cert_overflow(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ cumb, int min_cams, double thr,
+                double init_best, RansacSlot* __restrict__ slots, const double2* __restrict__ rec,
+                const unsigned int* __restrict__ over, const unsigned int* __restrict__ n_over,
+                unsigned int* __restrict__ counter) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const int F = cert_record_fields(C);
+  const double T1 = thr < init_best ? thr : init_best;
+  const int lane = threadIdx.x & 31;
+  const unsigned int total = *n_over;
+#pragma unroll 1
+  for (;;) {
+    unsigned int i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1u);
+    i = __shfl_sync(FULLM, i, 0);
+    if (i >= total) break;
+    const unsigned int q = over[i];
+    const double2* r = rec + ((size_t)(q >> 5) * F) * 32 + (q & 31u);
+    XY raw[CC], xh[CC];
+    uint32_t badrow[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      if (c < C) {
+        const double2 a = r[(size_t)c * 32], b = r[(size_t)(C + c) * 32];
+        raw[c].x = a.x, raw[c].y = a.y;
+        xh[c].x = b.x, xh[c].y = b.y;
+      }
+    }
+    const uint4 m0 = reinterpret_cast<const uint4*>(r)[(size_t)(2 * C) * 32];
+    const uint32_t v = m0.x & 0xffffu, u = m0.x >> 16, idx = m0.y;
+    uint32_t dcur = m0.z;
+    int pass = (int)(m0.w & 255u);
+    bool have = (m0.w & 256u) != 0;
+    uint32_t best_d = m0.w >> 16;
+    const double2 b0 = r[(size_t)(2 * C + 1) * 32], b1 = r[(size_t)(2 * C + 2) * 32];
+    double best_err = b0.x, bx = b0.y, by = b1.x, bz = b1.y;
+#pragma unroll
+    for (int g = 0; g < (CC + 7) / 8; ++g) {
+      if (8 * g < C) {
+        const uint4 w = reinterpret_cast<const uint4*>(r)[(size_t)(2 * C + 3 + g) * 32];
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (8 * g + 2 * j < CC) badrow[8 * g + 2 * j] = pass == 2 ? 0u : (ww[j] & 0xffffu);
+          if (8 * g + 2 * j + 1 < CC) badrow[8 * g + 2 * j + 1] = pass == 2 ? 0u : (ww[j] >> 16);
+        }
+      }
+    }
+    // lane-local best of pass 2 (every lane starts from the point's running best)
+    double l_err = best_err, lx = bx, ly = by, lz = bz;
+    uint32_t l_d = best_d;
+    bool l_have = false, stopped = false, ran_out = false;
+#pragma unroll 1
+    for (;;) {
+      if (dcur == 0) {
+        if (pass == 1 && T1 < best_err) {
+          pass = 2;
+#pragma unroll
+          for (int p = 0; p < CC; ++p) badrow[p] = 0;
+          dcur = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+          if (dcur != 0) continue;
+        }
+        ran_out = true;
+        break;
+      }
+      // lane j: the j-th surviving subset from dcur on (0 once the enumeration is exhausted)
+      uint32_t mine = dcur;
+      if (pass == 2) {  // no pruning: the next admissible mask
+#pragma unroll 1
+        for (int t = 0; t < lane && mine != 0; ++t) {
+          do {
+            mine = cert_next(v, mine);
+          } while (mine != 0 && __popc(v & ~mine) < min_cams);
+        }
+      } else {
+#pragma unroll 1
+        for (int t = 0; t < lane; ++t)
+          if (mine != 0) mine = cert_advance<NC>(v, cert_next(v, mine), badrow, min_cams);
+      }
+      double X = qnan(), Y = qnan(), Z = qnan(), err = qnan();
+      if (mine != 0) {
+        const uint32_t kept = v & ~mine;
+        err = cert_eval<PO, NC>(rig, raw, xh, kept, kept & u, X, Y, Z);
+      }
+      if (pass == 1) {
+        const uint32_t okb = __ballot_sync(FULLM, mine != 0 && err < T1);
+        if (okb) {  // first subset in enumeration order under T1: the reference stops here
+          const int src = __ffs(okb) - 1;
+          best_err = __shfl_sync(FULLM, err, src);
+          bx = __shfl_sync(FULLM, X, src);
+          by = __shfl_sync(FULLM, Y, src);
+          bz = __shfl_sync(FULLM, Z, src);
+          best_d = __shfl_sync(FULLM, mine, src);
+          have = true;
+          stopped = true;
+          break;
+        }
+      } else if (mine != 0 && err < l_err) {
+        l_err = err, l_d = mine, lx = X, ly = Y, lz = Z, l_have = true;
+      }
+      const uint32_t last = __shfl_sync(FULLM, mine, 31);
+      dcur = last != 0 ? cert_advance<NC>(v, cert_next(v, last), badrow, min_cams) : 0u;
+    }
+    if (!stopped && pass == 2) {
+      // strict arg-min over the lanes, the lower step index (= lower d) on ties
+      double e = l_have ? l_err : pos_inf();
+      uint32_t dd = l_have ? l_d : 0xffffffffu;
+      int src = lane;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double e2 = __shfl_xor_sync(FULLM, e, off);
+        const uint32_t d2 = __shfl_xor_sync(FULLM, dd, off);
+        const int s2 = __shfl_xor_sync(FULLM, src, off);
+        if (e2 < e || (e2 == e && d2 < dd)) e = e2, dd = d2, src = s2;
+      }
+      if (e < best_err) {
+        best_err = e;
+        best_d = dd;
+        bx = __shfl_sync(FULLM, lx, src);
+        by = __shfl_sync(FULLM, ly, src);
+        bz = __shfl_sync(FULLM, lz, src);
+        have = true;
+      }
+    }
+    if (lane == 0) {
+      const int k = __popc(v);
+      const uint32_t s_sel = cert_step_index<NC>(v, best_d);
+      int ne = 1;
+      if (ran_out) ne += count_adm(cumb, (1u << k) - 1u, k - min_cams);
+      else ne += count_adm(cumb, s_sel, k - min_cams);
+      RansacSlot* sl = slots + idx;
+      sl->best_err = best_err;
+      sl->bx = bx;
+      sl->by = by;
+      sl->bz = bz;
+      sl->best_s = have ? (int32_t)s_sel : -1;
+      sl->neval = ne;
     }
   }
 }
