@@ -1,0 +1,73 @@
+"""GPU tier, N > 1: the frame-sharded subset RANSAC over NCCL (one process per GPU, round-robin
+tiles, per-round gather into rank 0's frame-ordered arrays) returns bit-for-bit what one GPU returns
+for the whole recording.  Needs two visible GPUs (the driver's single-GPU box skips it; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_frames, tile, ransac, tmp):
+    import torch
+    import torch.distributed as dist
+    from macaque_3d_pose_estimation_b200 import sharding, synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dicts = synth.make_rig(8, "pinhole", seed=20261020)
+        cg = CameraGroup.from_dicts(dicts)
+        cg.device = rank
+        cams = fixtures.cams_from_dicts(dicts)
+        X = synth.make_tracks(n_frames, 2, seed=3).reshape(-1, 3)
+        p2 = synth.corrupt(og.project(cams, X), seed=3, p_outlier=0.2 if ransac else 0.0, p_missing=0.1)
+        tl = tile
+        if tl == "auto":
+            even = max(1, -(-n_frames // world))
+            tl = max(sharding.RANSAC_TILE_FRAMES, -(-even // 16)) if ransac else even
+        local = torch.from_numpy(np.ascontiguousarray(sharding.shard_points(p2, n_frames, rank, world, tl))).cuda()
+        p3d, err = sharding.triangulate_sharded(cg, local, n_frames, ransac=ransac, tile_frames=tile)
+        if rank == 0:
+            full = torch.from_numpy(p2).cuda()
+            if ransac:
+                r3, _, _, re_ = cg.triangulate_ransac(full)
+            else:
+                r3, re_ = cg.triangulate_with_error(full)
+            np.savez(tmp, ok3=bool(torch.equal(p3d.nan_to_num(), r3.nan_to_num())),
+                     oke=bool(torch.equal(err.nan_to_num(), re_.nan_to_num())), n=int(p3d.shape[0]))
+        else:
+            assert p3d is None and err is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames,tile,ransac", [(3000, 97, True), (700, "auto", True), (1000, "auto", False), (5, 256, True)])
+def test_nccl_sharded_equals_single_gpu(tmp_path, n_frames, tile, ransac):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 visible GPUs (this box has %d): NCCL multi-rank parity is run with gpurun --gpus 2"
+                    % torch.cuda.device_count())
+    import __graft_entry__ as ge
+    ge.build_library()
+    tmp = str(tmp_path / "out.npz")
+    mp.spawn(_worker, args=(2, _free_port(), n_frames, tile, ransac, tmp), nprocs=2, join=True)
+    r = np.load(tmp)
+    assert r["n"] == n_frames * 34
+    assert bool(r["ok3"]) and bool(r["oke"]), "sharded result differs from the single-GPU result"
