@@ -105,6 +105,16 @@ int m3d_undistort(const m3d_rig* rig, const double* xy_dev, int64_t N, double* o
 /* CameraGroup.project (cameras.py:580-591): p3d_dev (N,3) -> out_dev (C,N,2). */
 int m3d_project(const m3d_rig* rig, const double* p3d_dev, int64_t N, double* out_dev,
                 void* stream);
+/* Values of the `undistort` argument of m3d_triangulate / m3d_triangulate_error(_host):
+ *   0                    points are already undistorted (cameras.py:615 `undistort=False`)
+ *   M3D_UNDISTORT        the reference's per-camera undistortion, float64 throughout (default)
+ *   M3D_UNDISTORT_FAST   opt-in: the first three of OpenCV's five fixed-point iterations in float32.
+ *                        Results stay inside the tolerances BASELINE.json states (1e-4 relative or
+ *                        0.01 mm, 1e-3 px; measured ~1e-6 mm / 3e-5 px) but are no longer the
+ *                        float64 values bit for bit; plain pinhole rigs only (others run the strict
+ *                        path); the subset RANSAC always runs strict. */
+#define M3D_UNDISTORT 1
+#define M3D_UNDISTORT_FAST 3
 /* CameraGroup.triangulate (cameras.py:593-637): xy_dev (C,N,2) -> p3d_dev (N,3).
  * undistort != 0 applies the per-camera undistortion first.  A camera is used for a
  * point iff its (undistorted) x is not NaN; fewer than two -> (NaN,NaN,NaN). */

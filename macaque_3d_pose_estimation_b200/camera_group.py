@@ -20,6 +20,11 @@ class CameraGroup:
         self.metadata = metadata
         self.device = device
         self._rig_cache = None
+        # opt-in (not part of the reference API): run the first three of OpenCV's five
+        # undistortion iterations in float32 inside triangulate / triangulate_with_error
+        # (M3D_UNDISTORT_FAST of include/m3d.h: results within BASELINE.json's tolerances, not
+        # bit-identical to the float64 path).  The subset RANSAC ignores it.
+        self.fast_undistort = False
 
     # -- bookkeeping --
     def _dev(self):
@@ -134,6 +139,11 @@ class CameraGroup:
         self._assert_cams(points)
         return self._triangulate_error(points, undistort, with_err=True)
 
+    def _undistort_flag(self, undistort):
+        if not undistort:
+            return 0
+        return 3 if self.fast_undistort else 1          # M3D_UNDISTORT_FAST / M3D_UNDISTORT
+
     def _triangulate_error(self, points, undistort, with_err):
         C = len(self.cameras)
         n = points.shape[1]
@@ -144,14 +154,14 @@ class CameraGroup:
             src = np.ascontiguousarray(points, dtype=np.float64)
             p3d = np.empty((n, 3))
             err = np.empty(n) if with_err else None
-            _lib.check(rig._lib.m3d_triangulate_error_host(rig.handle, _np_ptr(src), n, int(bool(undistort)),
+            _lib.check(rig._lib.m3d_triangulate_error_host(rig.handle, _np_ptr(src), n, self._undistort_flag(undistort),
                                                            _np_ptr(p3d), _np_ptr(err)),
                        "m3d_triangulate_error_host")
             return p3d, err
         src = _to_dev(points, device)
         p3d = torch.empty((n, 3), dtype=torch.float64, device=src.device)
         err = torch.empty((n,), dtype=torch.float64, device=src.device) if with_err else None
-        _lib.check(rig._lib.m3d_triangulate_error(rig.handle, _ptr(src), n, int(bool(undistort)),
+        _lib.check(rig._lib.m3d_triangulate_error(rig.handle, _ptr(src), n, self._undistort_flag(undistort),
                                                   _ptr(p3d), _ptr(err), _stream(device)),
                    "m3d_triangulate_error")
         return p3d, err

@@ -155,7 +155,9 @@ k_project(const __grid_constant__ RigDev rig, int cam0, int ncam, const double* 
 // camera parameter becomes a constant-bank operand of the DFMA that uses it (no LDC, no
 // register), and the raw observations stay in registers for the error pass.
 // NC == 0: run-time camera count (any rig up to M3D_MAX_CAMS).
-template <bool FULL, bool PO, bool UNDISTORT, bool WITH_ERR, int NC, int MINB>
+// FAST: undistort_pinhole_fast (float32 in the first three iterations; opt-in, pinhole-only rigs
+// without rational / thin-prism terms).
+template <bool FULL, bool PO, bool UNDISTORT, bool WITH_ERR, int NC, int MINB, int FAST = 0>
 __global__ void __launch_bounds__(256, MINB)
 k_triangulate(const __grid_constant__ RigDev rig, const double* __restrict__ xy, int64_t N,
               double* __restrict__ p3d, double* __restrict__ err) {
@@ -172,7 +174,10 @@ k_triangulate(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         double x = raw[c].x, y = raw[c].y;
-        if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], raw[c].x, raw[c].y, x, y);
+        if (UNDISTORT) {
+          if (FAST) undistort_pinhole_fast<FAST>(rig.cam[c], raw[c].x, raw[c].y, x, y);
+          else undistort_point<FULL, PO>(rig.cam[c], raw[c].x, raw[c].y, x, y);
+        }
         if (x == x) {  // validity on x only (cameras.py:630)
           gram_add_camera(G, rig.cam[c], x, y);
           ++cnt;
@@ -200,7 +205,10 @@ k_triangulate(const __grid_constant__ RigDev rig, const double* __restrict__ xy,
       for (int c = 0; c < C; ++c) {
         const double2 p = ld_xy(xy, (int64_t)c * N + n);
         double x = p.x, y = p.y;
-        if (UNDISTORT) undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+        if (UNDISTORT) {
+          if (FAST) undistort_pinhole_fast<FAST>(rig.cam[c], p.x, p.y, x, y);
+          else undistort_point<FULL, PO>(rig.cam[c], p.x, p.y, x, y);
+        }
         if (x == x) {
           gram_add_camera(G, rig.cam[c], x, y);
           ++cnt;
@@ -574,6 +582,26 @@ static int launch_triangulate(const m3d_rig* rig, const double* xy, int64_t N, i
   const int grid = grid_for(N, 256, sms);
   const int C = rig->dev.n_cams;
   M3dKernelTimer timer__("k_triangulate", st);
+  // opt-in north-star-tolerance path (M3D_UNDISTORT_FAST): plain pinhole rigs only, else strict
+  const bool fast = (undistort & 2) != 0 && (rig->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM | RIG_HAS_NONPINHOLE)) == 0;
+  if (fast) {
+    // float32 iterations of the five (developer switch M3D_FAST_ITERS = 3 | 4 | 5; default 4)
+    static const int fast_iters = [] { const char* e = getenv("M3D_FAST_ITERS"); return e ? atoi(e) : 4; }();
+#define CALLF(NC, MB, NF)                                                                                          \
+  do {                                                                                                             \
+    if (err) k_triangulate<false, true, true, true, NC, MB, NF><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);  \
+    else k_triangulate<false, true, true, false, NC, MB, NF><<<grid, 256, 0, st>>>(rig->dev, xy, N, p3d, err);     \
+  } while (0)
+    if (C == 8) {
+      if (fast_iters == 3) CALLF(8, 2, 3);
+      else if (fast_iters == 5) CALLF(8, 2, 5);
+      else CALLF(8, 2, 4);
+    } else {
+      CALLF(0, 3, 4);
+    }
+#undef CALLF
+    return check_launch("k_triangulate");
+  }
 #define CALLV(F, P, NC, MB)                                                                         \
   do {                                                                                              \
     if (undistort) {                                                                                \

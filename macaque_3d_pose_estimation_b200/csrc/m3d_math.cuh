@@ -39,6 +39,7 @@ struct CamDev {
   double xi;
   int32_t model;
   int32_t pad;
+  float kf[6];      // k1 k2 p1 p2 k3 in float32 (undistort_pinhole_fast), padding
 };
 
 struct RigDev {
@@ -183,6 +184,63 @@ M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, d
     y = (y0 - dy) * icdist;
   }
   if (neg < 0) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
+  xo = x;
+  yo = y;
+}
+
+// North-star-tolerance variant of undistort_pinhole (opt-in, M3D_UNDISTORT_FAST): the first three
+// of OpenCV's five fixed-point iterations run in float32 (FMA pipe, twice the rate of the fp64
+// pipe and issued beside it), the last two in float64 from the exact (x0, y0).  The iteration
+// contracts (factor <= ~0.25 inside the image for |k1| <= 0.25), so the float32 rounding of the
+// third iterate (~1e-7 relative) reaches the result damped by two more steps: measured <= 2e-8 in
+// normalised units = 3e-5 px (tests/test_gpu_parity.py asserts the north-star tolerances 1e-4 rel /
+// 0.01 mm / 1e-3 px against the reference goldens).  Plain 5-coefficient model only; the icdist < 0
+// bail-out replays the point through the literal float64 transcription exactly like the strict path.
+template <int NF32>
+M3D_HD void undistort_pinhole_fast(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double x0 = (u - c.cx) * c.ifx;
+  const double y0 = (v - c.cy) * c.ify;
+  const float x0f = (float)x0, y0f = (float)y0;
+  float xf = x0f, yf = y0f;
+  int neg = 0;
+#pragma unroll
+  for (int j = 0; j < NF32; ++j) {
+    const float r2 = xf * xf + yf * yf;
+    const float den = 1.0f + ((c.kf[4] * r2 + c.kf[1]) * r2 + c.kf[0]) * r2;
+#if defined(__CUDA_ARCH__)
+    float icd;  // MUFU.RCP (1 ulp): the contraction of the iteration absorbs it
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(icd) : "f"(den));
+    neg |= __float_as_int(icd);
+#else
+    const float icd = 1.0f / den;
+    neg |= (icd < 0.0f) ? -1 : 0;
+#endif
+    const float x2 = xf + xf, y2 = yf + yf;
+    const float xy2 = x2 * yf;
+    const float dx = c.kf[2] * xy2 + c.kf[3] * (x2 * xf + r2);
+    const float dy = c.kf[3] * xy2 + c.kf[2] * (y2 * yf + r2);
+    xf = (x0f - dx) * icd;
+    yf = (y0f - dy) * icd;
+  }
+  double x = (double)xf, y = (double)yf;
+#pragma unroll
+  for (int j = 0; j < 5 - NF32; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = rcp(1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
+#if defined(__CUDA_ARCH__)
+    neg |= __double2hiint(icdist);
+#else
+    neg |= (icdist < 0.0) ? -1 : 0;
+#endif
+    const double x2 = x + x, y2 = y + y;
+    const double xy2 = x2 * y;
+    const double dx = c.k[2] * xy2 + c.k[3] * (x2 * x + r2);
+    const double dy = c.k[3] * xy2 + c.k[2] * (y2 * y + r2);
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  // bail-out, or a float32 overflow on a finite input (|x0| > 1e6: far outside any image)
+  if (neg < 0 || (!(x == x) && u == u && v == v)) undistort_pinhole_exact<false>(c, u, v, x, y);
   xo = x;
   yo = y;
 }

@@ -67,6 +67,8 @@ inline std::string build_rig(const m3d_cam* cams, int n_cams, RigDev* rig) {
       for (int j = 0; j < 4; ++j) c.k[j] = in.dist[j];
       flags |= RIG_HAS_NONPINHOLE;
     }
+    for (int j = 0; j < 5; ++j) c.kf[j] = (float)c.k[j];
+    c.kf[5] = 0.0f;
     rodrigues(in.rvec, c.R);
     c.t[0] = in.tvec[0];
     c.t[1] = in.tvec[1];
