@@ -228,6 +228,32 @@ int m3d_viterbi_filter(const double* cand_dev, int64_t S, int64_t F, int32_t P, 
                        double thres_dist, double score_threshold, double dup_thres,
                        double* out_dev, int32_t* choice_dev, int32_t device, void* stream);
 
+/* ---- temporal / skeletal refinement of the 3D stage -------------------------------- */
+/* CameraGroup.optim_points and optim_points_jointlenfix (cameras.py:1116-1270; the default
+ * `optim = true` branch of step4_aniposefiltering.py:247-271) for ONE animal: minimise
+ *   rho(|score (p2d - project(P))|)  +  scale_smooth diff_n(P)  +  limb-length terms
+ * (the residual vector of _error_fun_triangulation, cameras.py:1560-1620) over the 3D points P (F,J,3)
+ * and, unless fix_lengths, the limb lengths.
+ *   p2d_dev (C,F,J,2) raw pixels, NaN = missing;  scores_dev (C,F,J) or NULL
+ *   constraints (K,2) / constraints_weak (Kw,2): HOST arrays of joint index pairs
+ *   loss: 0 linear, 1 soft_l1, 2 huber (reproj_loss);  n_deriv_smooth: order of the temporal difference
+ *   params_dev: [P (F*J*3) | L (K) | Lw (Kw)], the start point x0 on entry (the reference's
+ *               _initialize_params_triangulation), the solution on return (L | Lw are read-only when
+ *               fix_lengths != 0)
+ *   mode 0  solve: Levenberg-Marquardt with exact Jacobian blocks and a block-preconditioned CG inner
+ *           solve, until the relative cost decrease of an accepted step is < ftol or max_iter steps;
+ *           info_host[0..5] = final cost (0.5 |r|^2), initial cost, LM steps, CG iterations, residual
+ *           evaluations, status (1 stationary, 2 ftol reached, 3 no further decrease, 0 max_iter)
+ *   mode 1  out_dev <- residual vector at params: [r1 (C,F,J,2), NaN where p2d is NaN | r2 ((F-n),J,3) |
+ *           r3 (K,F) | r4 (Kw,F)] — the reference's vector is this with the NaN entries dropped
+ *   mode 2  out_dev holds a parameter-space vector v on entry and J v (same dense layout) on return */
+int m3d_optim_points(const m3d_rig* rig, const double* p2d_dev, const double* scores_dev, int32_t F,
+                     int32_t J, const int32_t* constraints, int32_t K, const int32_t* constraints_weak,
+                     int32_t Kw, double scale_smooth, double scale_length, double scale_length_weak,
+                     double reproj_error_threshold, int32_t loss, int32_t n_deriv_smooth,
+                     int32_t fix_lengths, double ftol, int32_t max_iter, int32_t mode,
+                     double* params_dev, double* out_dev, double* info_host, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Number of kernels this library has launched on the calling process (bench.py's
  * gpu_launches). */

@@ -321,12 +321,28 @@ class CameraGroup:
             cgroup.metadata = doc['metadata']
         return cgroup
 
-    # -- out of scope --
-    def optim_points(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE % ("optim_points", "1116-1190"))
+    # -- temporal / skeletal refinement --
+    def optim_points(self, points, p3ds, constraints=[], constraints_weak=[], scale_smooth=4, scale_length=2,
+                     scale_length_weak=0.5, reproj_error_threshold=15, reproj_loss='soft_l1', n_deriv_smooth=1,
+                     scores=None, verbose=False, **solver):
+        """Take in an array of 2D points of shape CxNxJx2, an array of 3D points of shape NxJx3 and
+        constraints of shape Kx2; returns the optimised NxJx3 points and the limb lengths
+        (cameras.py:1116-1190) — GPU Levenberg-Marquardt, see optim.py."""
+        from . import optim
+        return optim.optim_points(self, points, p3ds, constraints, constraints_weak, scale_smooth, scale_length,
+                                  scale_length_weak, reproj_error_threshold, reproj_loss, n_deriv_smooth, scores,
+                                  verbose, None, **solver)
 
-    def optim_points_jointlenfix(self, *a, **k):
-        raise NotImplementedError(_OUT_OF_SCOPE % ("optim_points_jointlenfix", "1192-1270"))
+    def optim_points_jointlenfix(self, points, p3ds, joint_len, constraints=[], constraints_weak=[], scale_smooth=4,
+                                 scale_length=2, scale_length_weak=0.5, reproj_error_threshold=15,
+                                 reproj_loss='soft_l1', n_deriv_smooth=1, scores=None, verbose=False, **solver):
+        """optim_points with the limb lengths held at ``joint_len`` (cameras.py:1192-1270)."""
+        from . import optim
+        return optim.optim_points(self, points, p3ds, constraints, constraints_weak, scale_smooth, scale_length,
+                                  scale_length_weak, reproj_error_threshold, reproj_loss, n_deriv_smooth, scores,
+                                  verbose, np.asarray(joint_len, dtype=np.float64), **solver)
+
+    # -- out of scope --
 
     def bundle_adjust(self, *a, **k):
         raise NotImplementedError(_OUT_OF_SCOPE % ("bundle_adjust", "860-946"))

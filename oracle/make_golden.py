@@ -283,6 +283,71 @@ def case_viterbi(name, n_frames, n_joints, n_possible, seed, score_threshold=0.3
     print("%-28s F=%d J=%d P=%d  reference %.2f s" % (name, F, J, n_possible, dt))
 
 
+MACAQUE_CONSTRAINTS = [(0, 1), (0, 2), (1, 2), (0, 3), (0, 4), (1, 3), (2, 4), (3, 4), (5, 3), (6, 4), (5, 6), (5, 7),
+                       (7, 9), (6, 8), (8, 10), (11, 12), (11, 13), (13, 15), (12, 14), (14, 16)]
+MACAQUE_CONSTRAINTS_WEAK = [(5, 11), (6, 12), (5, 12), (6, 11), (5, 6), (11, 12), (1, 0), (2, 0), (1, 3), (2, 4), (3, 4)]
+
+
+def case_optim(ref, name, n_cams, n_frames, seed, n_deriv=2, reproj_loss="soft_l1", fix=False, with_scores=False):
+    """optim_points / optim_points_jointlenfix (cameras.py:1116-1270) on one synthetic animal with the
+    constraint lists and weights of configs/config_tmpl.toml:66-97: the reference's start vector, its
+    residual vector there and at a perturbed point, and what least_squares(ftol=1e-3) returns."""
+    cams = synth.make_rig(n_cams, "pinhole", seed=seed)
+    cg = ref.CameraGroup.from_dicts(cams)
+    rng = np.random.default_rng(seed)
+    X = synth.make_tracks(n_frames, 1, seed=seed)[:, 0]                       # (F, J, 3)
+    # a smooth track: the random walk of make_tracks + a slow limb motion
+    X = X + 30.0 * np.sin(np.arange(n_frames)[:, None, None] / 7.0 + rng.uniform(0, 6, (1, X.shape[1], 3)))
+    p2 = synth.corrupt(cg.project(X.reshape(-1, 3)), seed=seed, noise=0.8, p_outlier=0.03, sigma_outlier=25.0,
+                       p_missing=0.15)
+    pts = p2.reshape(n_cams, n_frames, X.shape[1], 2)
+    pts[0, 3, 2, 1] = np.nan                                                # y missing only: one residual dropped
+    p3d0 = cg.triangulate(pts.reshape(n_cams, -1, 2)).reshape(n_frames, -1, 3)
+    p3d0[5, 4] = np.nan                                                     # a gap the interpolation fills
+    p3d0[9:12, 7] = np.nan
+    scores = rng.uniform(0.5, 1.0, size=pts.shape[:3]) if with_scores else None
+    kw = dict(scale_smooth=3, scale_length=5, scale_length_weak=2, n_deriv_smooth=n_deriv, reproj_error_threshold=3,
+              reproj_loss=reproj_loss)
+    cons, consw = np.array(MACAQUE_CONSTRAINTS), np.array(MACAQUE_CONSTRAINTS_WEAK)
+    intp = np.apply_along_axis(ref.interpolate_data, 0, p3d0)
+    med = np.apply_along_axis(ref.medfilt_data, 0, intp, size=7)
+    s_full = kw["scale_smooth"] * (1.0 / np.mean(np.abs(np.diff(med, axis=0))))
+    x0 = cg._initialize_params_triangulation(intp, cons, consw)
+    x0[~np.isfinite(x0)] = 0
+    args = (pts, cons, consw, scores, s_full, kw["scale_length"], kw["scale_length_weak"],
+            kw["reproj_error_threshold"], reproj_loss, n_deriv)
+    r0 = np.array(cg._error_fun_triangulation(x0, *args))
+    x1 = x0 + rng.normal(0, 2.0, x0.shape)
+    r1 = np.array(cg._error_fun_triangulation(x1, *args))
+    out = dict(rig_arrays(cams), points=pts, p3d0=p3d0, intp=intp, scale_smooth_full=s_full, x0=x0, r0=r0, x1=x1,
+               r1=r1, constraints=cons, constraints_weak=consw, n_deriv=n_deriv, fix=int(fix),
+               reproj_loss=np.array(reproj_loss), **{k: v for k, v in kw.items() if k != "reproj_loss"})
+    if scores is not None:
+        out["scores"] = scores
+    t0 = time.time()
+    if fix:
+        jl = x0[intp.size:]
+        new, jl_out = cg.optim_points_jointlenfix(pts, p3d0, jl, constraints=cons, constraints_weak=consw, scores=scores, **kw)
+        rf = np.array(cg._error_fun_triangulation_jointlenfix(new.ravel(), pts, jl, cons, consw, scores, s_full,
+                                                               kw["scale_length"], kw["scale_length_weak"],
+                                                               kw["reproj_error_threshold"], reproj_loss, n_deriv))
+        out["r0_fix"] = np.array(cg._error_fun_triangulation_jointlenfix(
+            x0[:intp.size], pts, jl, cons, consw, scores, s_full, kw["scale_length"], kw["scale_length_weak"],
+            kw["reproj_error_threshold"], reproj_loss, n_deriv))
+    else:
+        new, jl_out = cg.optim_points(pts, p3d0, constraints=cons, constraints_weak=consw, scores=scores, **kw)
+        rf = np.array(cg._error_fun_triangulation(np.hstack([new.ravel(), jl_out]), *args))
+    out["ref_seconds"] = time.time() - t0
+    out["opt_p3d"] = new
+    out["opt_joint_len"] = jl_out
+    out["opt_cost"] = 0.5 * float(rf @ rf)
+    out["x0_cost"] = 0.5 * float(r0 @ r0)
+    out["X_true"] = X
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("%-28s F=%d  cost %.6g -> %.6g  reference %.1f s" % (name, n_frames, out["x0_cost"], out["opt_cost"],
+                                                              out["ref_seconds"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -321,6 +386,10 @@ def main():
         "viterbi_p1": lambda: case_viterbi("viterbi_p1", 400, 6, 1, S + 31),
         "viterbi_p2": lambda: case_viterbi("viterbi_p2", 150, 4, 2, S + 32),
         "viterbi_p1_nb4": lambda: case_viterbi("viterbi_p1_nb4", 120, 3, 1, S + 33, n_back=4, offset_threshold=10),
+        "optim_c8_n2": lambda: case_optim(ref, "optim_c8_n2", 8, 48, S + 51),
+        "optim_c4_n1_huber": lambda: case_optim(ref, "optim_c4_n1_huber", 4, 30, S + 52, n_deriv=1, reproj_loss="huber",
+                                                with_scores=True),
+        "optim_c8_fix": lambda: case_optim(ref, "optim_c8_fix", 8, 36, S + 53, fix=True),
     }
     for name, fn in cases.items():
         if args.only and args.only != name:
