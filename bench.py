@@ -253,6 +253,57 @@ def cpu_baseline(workload, n_cams, with_all_cores):
     return out
 
 
+def optim_line(cx, args):
+    """Step-4 refinement (CameraGroup.optim_points, the default branch of the reference's 3D stage): one animal,
+    8 views, the template's constraints and weights; GPU solver against the port of the reference's
+    scipy.optimize.least_squares call on the same data (a shorter clip: its cost grows faster than linearly)."""
+    import numpy as np
+    from macaque_3d_pose_estimation_b200 import synth
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    from oracle import make_golden as mg
+    from oracle import optim as oopt
+
+    def clip(F, seed):
+        dicts = synth.make_rig(args.cameras, "pinhole", seed=20261018 + 2)
+        cams = fixtures.cams_from_dicts(dicts)
+        rng = np.random.default_rng(seed)
+        X = synth.make_tracks(F, 1, seed=seed)[:, 0] * np.array([0.6, 0.6, 0.5])
+        X = X + 30.0 * np.sin(np.arange(F)[:, None, None] / 7.0 + rng.uniform(0, 6, (1, X.shape[1], 3)))
+        p2 = synth.corrupt(og.project(cams, X.reshape(-1, 3)), seed=seed, noise=0.8, p_outlier=0.03,
+                           sigma_outlier=25.0, p_missing=0.15)
+        return cams, p2.reshape(args.cameras, F, X.shape[1], 2)
+    kw = dict(constraints=mg.MACAQUE_CONSTRAINTS, constraints_weak=mg.MACAQUE_CONSTRAINTS_WEAK, scale_smooth=3,
+              scale_length=5, scale_length_weak=2, n_deriv_smooth=2, reproj_error_threshold=3)
+    out = {}
+    try:
+        F = 20000
+        cams, pts = clip(F, 77)
+        init = cx.cg.triangulate(pts.reshape(args.cameras, -1, 2)).reshape(F, -1, 3)
+        cx.cg.optim_points(pts[:, :200], init[:200], **kw)                    # warm-up
+        t0 = time.perf_counter()
+        new, jl, info = cx.cg.optim_points(pts, init, return_info=True, **kw)
+        dt = time.perf_counter() - t0
+        out = {"workload": "optim_points: 1 animal x 17 joints x %d frames, %d views, 20 strong + 11 weak limb "
+                           "constraints, n_deriv_smooth 2 (config_tmpl.toml defaults)" % (F, args.cameras),
+               "value": F / dt, "unit": "frames/s (one GPU, host arrays in and out)", "seconds": dt,
+               "cost0": info["cost0"], "cost": info["cost"], "lm_steps": info["lm_steps"],
+               "cg_iterations": info["cg_iterations"], "residual_evaluations": info["evaluations"]}
+        if not args.no_cpu:
+            Fc = 200
+            t0 = time.perf_counter()
+            pn, pj, pcost = oopt.optim_points_port(cams, pts[:, :Fc], init[:Fc], **kw)
+            dtc = time.perf_counter() - t0
+            g2, gj, ginfo = cx.cg.optim_points(pts[:, :Fc], init[:Fc], return_info=True, **kw)
+            out["cpu_baseline"] = {"value": Fc / dtc, "unit": "frames/s", "cores": 1, "kind": "port", "seconds": dtc,
+                                   "sample": "%d frames of the same clip through scipy.optimize.least_squares exactly as "
+                                             "the reference calls it (oracle/optim.py optim_points_port)" % Fc,
+                                   "final_cost": pcost, "gpu_final_cost_same_clip": ginfo["cost"]}
+    except Exception as ex:  # pragma: no cover
+        out = {"error": str(ex)[:300]}
+    return out
+
+
 def config_dict(workload, C, frames_per_gpu, n_gpus, extra=None):
     d = {"workload": NAMES[workload] % C, "cameras": C, "camera_model": "pinhole(5 coeff)",
          "joint_instances_per_gpu": int(frames_per_gpu * ANIMALS * JOINTS), "frames_per_gpu": int(frames_per_gpu),
@@ -719,6 +770,8 @@ def run_gpu(args):
         if k in head:
             line[k] = head[k]
     line.update(head["extra"])
+    if cx.world == 1 and not args.only:
+        line["optim_points"] = optim_line(cx, args)
     if second is not None:
         key = "cfg2" if other == "dlt" else "cfg3"
         sec = {k: second[k] for k in ("value", "ms_per_step", "gpu_launches", "config", "roofline", "e2e") if k in second}

@@ -436,7 +436,15 @@ __global__ void __launch_bounds__(256) k_dot(const double* __restrict__ a, const
     if (!skip_nan || x == x) acc += x;
   }
   acc = block_sum(acc);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) out[1 + blockIdx.x] = acc;  // per-block partials, summed in a fixed order below
+}
+// out[0] = sum of the nb per-block partials out[1 .. nb], always in the same order: the solver is
+// deterministic from run to run (no floating-point atomics anywhere on its path)
+__global__ void __launch_bounds__(256) k_dot_final(double* __restrict__ out, int nb) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += out[1 + i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) out[0] = acc;
 }
 // y = alpha x + beta y
 __global__ void __launch_bounds__(256) k_axpby(double alpha, const double* __restrict__ x, double beta,
@@ -506,8 +514,9 @@ struct Optim {
   Ptrs ptrs() const { return {jac, gu, dL, cons, adj_off, adj_k, adj_sgn}; }
 
   double dot(const double* a, const double* b, int64_t n, bool skip_nan = false) {
-    cudaMemsetAsync(scal, 0, sizeof(double), st);
-    if (n > 0) k_dot<<<blocks_for(n, 256), 256, 0, st>>>(a, b, n, scal, skip_nan ? 1 : 0);
+    const int nb = n > 0 ? blocks_for(n, 256) : 0;
+    if (nb > 0) k_dot<<<nb, 256, 0, st>>>(a, b, n, scal, skip_nan ? 1 : 0);
+    k_dot_final<<<1, 256, 0, st>>>(scal, nb);
     double h = 0.0;
     cudaMemcpyAsync(&h, scal, sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
@@ -609,7 +618,7 @@ int m3d_optim_points(const m3d_rig* rig, const double* p2d_dev, const double* sc
   OPT_CUDA(o.alloc(&o.adj_off, adj_off.size()));
   OPT_CUDA(o.alloc(&o.adj_k, adj_k.size()));
   OPT_CUDA(o.alloc(&o.adj_sgn, adj_sgn.size()));
-  OPT_CUDA(o.alloc(&o.scal, 4));
+  OPT_CUDA(o.alloc(&o.scal, 148 * 16 + 4));
   OPT_CUDA(cudaMemcpyAsync(o.cons, cons.data(), sizeof(int) * cons.size(), cudaMemcpyHostToDevice, o.st));
   OPT_CUDA(cudaMemcpyAsync(o.adj_off, adj_off.data(), sizeof(int) * adj_off.size(), cudaMemcpyHostToDevice, o.st));
   if (!adj_k.empty()) {

@@ -75,8 +75,8 @@ def test_host_side_api_mirrors_reference():
         cg.triangulate_ransac(np.zeros((3, 4, 2)))
     with pytest.raises(AssertionError, match="not consistent"):
         cg.reprojection_error(np.zeros((5, 3)), np.zeros((8, 4, 2)))
-    with pytest.raises(NotImplementedError, match="1116"):
-        cg.optim_points()
+    with pytest.raises(NotImplementedError, match="860"):
+        cg.bundle_adjust()
     d = cg.cameras[0].get_dict()
     assert set(d) == {"name", "size", "matrix", "distortions", "rotation", "translation"}
     cam = Camera.from_dict(d)
