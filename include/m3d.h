@@ -34,7 +34,8 @@ extern "C" {
 
 #define M3D_MAX_CAMS 16
 #define M3D_MAX_JOINTS 32   /* keypoints per detection in m3d_ray_affinity */
-#define M3D_MAX_DETS 128    /* detections per frame in m3d_ray_affinity / m3d_match_svt */
+#define M3D_MAX_DETS 128    /* detections per frame in m3d_ray_affinity */
+#define M3D_MAX_DETS_SVT 112 /* detections per frame in m3d_match_svt (shared-memory limit of its Jacobi SVD) */
 
 #define M3D_OK 0
 #define M3D_ERR_INVALID -1  /* bad argument (shape, NULL, unsupported parameter)        */
@@ -209,6 +210,18 @@ int m3d_match_svt(const double* W_dev, const int32_t* dim_dev, int32_t F, int32_
                   int32_t C, double alpha, double lambda, double mu, double tol,
                   int32_t max_iter, uint8_t* match_dev, int32_t* iters_dev, int32_t device,
                   void* stream);
+
+/* Association weights of MultiEstimator.predict_data (step2_crossviewmatching.py:557-575) for F
+ * keyframes: W = alpha_id * [same identity in different cameras] + (1 - alpha_id) * aff, zero where
+ * aff <= 0 or NaN.  aff_dev (F,M,M), cid_dev (F,M) i32 identity label or -1, W_dev (F,M,M). */
+int m3d_association_weights(const double* aff_dev, const int32_t* cid_dev, const int32_t* dim_dev,
+                            int32_t F, int32_t M, int32_t C, double alpha_id, double* W_dev,
+                            int32_t device, void* stream);
+/* Person clusters of the match matrices (step2_crossviewmatching.py:598-607): a column with sum > 1.9
+ * is a person, a detection belongs to the first person column it is matched to.
+ * label_dev (F,M) i32: that column index, -1 = unmatched (or padding). */
+int m3d_match_clusters(const uint8_t* match_dev, const int32_t* dim_dev, int32_t F, int32_t M, int32_t C,
+                       int32_t* label_dev, int32_t device, void* stream);
 
 /* ---- 2D keypoint filter of the step-4 stage ---------------------------------------- */
 /* anipose filter_pose.viterbi_path (src/third_party/anipose/filter_pose.py:48-120, with

@@ -68,6 +68,8 @@ SIGNATURES = {
     "m3d_ray_affinity": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _D, _P, _P, _P]),
     "m3d_triangulate_ls": (ctypes.c_int, [_P, _P, _P, _L, _P, _P]),
     "m3d_match_svt": (ctypes.c_int, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _I, _P, _P, _I, _P]),
+    "m3d_association_weights": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _D, _P, _I, _P]),
+    "m3d_match_clusters": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "m3d_viterbi_filter": (ctypes.c_int, [_P, _L, _L, _I, _I, _D, _D, _D, _P, _P, _I, _P]),
     "m3d_optim_points": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _I, _P, _I, _D, _D, _D, _D, _I, _I, _I, _D, _I, _I,
                                         _P, _P, _P, _P]),

@@ -182,7 +182,7 @@ def calc_3dpose(kp_2d, config_path=None, camparam=None, thr_kp=THR_KP):
 
 
 # ------------------------------------------------------------------------------------------
-# keyframe association (MultiEstimator.predict_data, step2_crossviewmatching.py:502-713)
+# keyframe association, batched over keyframes (MultiEstimator.predict_data, step2:502-713)
 # ------------------------------------------------------------------------------------------
 
 ALPHA_ID = 0.2          # step2:22
@@ -195,107 +195,197 @@ def reproject(i_cam, p3d, camparam=None, config_path=""):
     return cg.cameras[i_cam].project(np.asarray(p3d, dtype=np.float64)).reshape(-1, 2)
 
 
+def _cam_of(dim, M):
+    """Camera index of every detection slot from the cumulative counts: dim (F,C+1) -> (F,M); padding
+    slots (m >= dim[:, C]) get C."""
+    return (np.arange(M)[None, :, None] >= dim[:, None, 1:]).sum(axis=2)
+
+
+def _undistort_detections(cgroup, kp_raw, cam_of, n_cams):
+    """Undistort the keypoints of all detections of all frames, one launch per camera."""
+    F, M, J, _ = kp_raw.shape
+    und = np.full((F, M, J, 2), np.nan)
+    for c in range(n_cams):
+        sel = cam_of == c
+        if sel.any():
+            pts = np.ascontiguousarray(kp_raw[sel][:, :, :2])                      # (n, J, 2)
+            und[sel] = cgroup.cameras[c].undistort_points(pts.reshape(1, -1, 2)).reshape(-1, J, 2)
+    return und
+
+
+def _ls_persons(cgroup, und_sel, score_sel, thr_kp):
+    """und_sel (P, C, J, 2), score_sel (P, C, J) -> (P, J, 3): calc_3dpose (step2:436-461) for P persons in
+    one launch (a camera without a member has score 0 everywhere)."""
+    P, C, J, _ = und_sel.shape
+    xy = np.ascontiguousarray(und_sel.transpose(1, 0, 2, 3)).reshape(C, P * J, 2)
+    sc = np.ascontiguousarray(score_sel.transpose(1, 0, 2)).reshape(C, P * J)
+    with np.errstate(invalid="ignore"):
+        use = ~(np.isnan(xy[:, :, 0]) | (sc < thr_kp) | np.isnan(sc))
+    return triangulate_ls_batch(cgroup, np.nan_to_num(xy), use).reshape(P, J, 3)
+
+
+def _combo_rmse(cgroup, kp_raw_sel, p3d, thr_kp):
+    """Reprojection RMSE of get_best_comb (step2:626-641): kp_raw_sel (P, C, J, 3) raw pixels + score (score
+    0 = camera not in the combination), p3d (P, J, 3) -> (P,) over the keypoints with score > thr."""
+    P, C, J, _ = kp_raw_sel.shape
+    proj = cgroup.project(p3d.reshape(-1, 3)).reshape(C, P, J, 2).transpose(1, 0, 2, 3)
+    keep = kp_raw_sel[..., 2] > thr_kp
+    d2 = ((kp_raw_sel[..., :2] - proj) ** 2).sum(axis=-1)
+    n = 2.0 * keep.sum(axis=(1, 2))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(n > 0, np.sqrt(np.where(keep, d2, 0.0).sum(axis=(1, 2)) / np.maximum(n, 1)), np.inf)
+
+
+def associate_batch(cgroup, kp_raw, dim, cid=None, bbox_id=None, thr_kp=THR_KP, alpha_id=0.2, alpha_svt=0.5,
+                    lambda_svt=50.0):
+    """Cross-view association + reconstruction of F keyframes at once — what
+    MultiEstimator.predict_data (step2_crossviewmatching.py:502-713) does per keyframe.
+
+      kp_raw (F, M, J, 3)  raw pixels + score of every detection, grouped by camera (padding beyond dim[:, C])
+      dim    (F, C+1)      cumulative detection counts per camera (dimGroup)
+      cid    (F, M) int    identity label per detection or -1 (None: no identity term)
+      bbox_id (F, M) int   tracklet id reported back per person and camera (None: the detection index)
+
+    Device stages (all frames per launch): undistortion, ray affinity, association weights, SVT matching,
+    cluster labels, least-squares triangulation, reprojection scoring of the duplicate combinations.  The
+    host only resolves clusters with two detections from one camera (rare) — by scoring ALL candidate
+    combinations of all frames in one batch.
+
+    Returns {'label' (F,M) person column per detection or -1, 'frame' (P,), 'members' (P,C) detection index
+    per camera or -1, 'p3d' (P,J,3), 'bcomb' (P,C)}; persons are ordered by frame, then like the reference
+    (ascending cluster column; a cluster's leftover combination follows its best one)."""
+    import itertools
+    kp_raw = np.asarray(kp_raw, dtype=np.float64)
+    dim = np.ascontiguousarray(dim, dtype=np.int32)
+    F, M, J, _ = kp_raw.shape
+    C = len(cgroup.cameras)
+    assert dim.shape == (F, C + 1)
+    device = cgroup._dev()
+    lib = _lib.require_gpu()
+    cam_of = _cam_of(dim, M)
+    und = _undistort_detections(cgroup, kp_raw, cam_of, C)
+    kp_und = np.concatenate([und, kp_raw[..., 2:3]], axis=-1)
+    dev = "cuda:%d" % device
+    aff = geometry_affinity_batch(cgroup, torch.from_numpy(np.nan_to_num(kp_und)).to(dev), dim, thr_kp)
+    d_dim = torch.from_numpy(dim).to(dev)
+    ids = np.full((F, M), -1, dtype=np.int32) if cid is None else np.ascontiguousarray(cid, dtype=np.int32)
+    d_cid = torch.from_numpy(ids).to(dev)
+    W = torch.empty_like(aff)
+    _lib.check(lib.m3d_association_weights(_ptr(aff), ctypes.c_void_p(d_cid.data_ptr()),
+                                           ctypes.c_void_p(d_dim.data_ptr()), F, M, C, float(alpha_id), _ptr(W),
+                                           int(device), _stream(device)), "m3d_association_weights")
+    match = match_svt_batch(W, d_dim, C, alpha=alpha_svt, _lambda=lambda_svt, device=device)
+    label = torch.empty((F, M), dtype=torch.int32, device=dev)
+    _lib.check(lib.m3d_match_clusters(ctypes.c_void_p(match.data_ptr()), ctypes.c_void_p(d_dim.data_ptr()), F, M, C,
+                                      ctypes.c_void_p(label.data_ptr()), int(device), _stream(device)),
+               "m3d_match_clusters")
+    label = label.cpu().numpy()
+
+    # ---- clusters -> one detection per camera (host bookkeeping on (F, M) integers) -----------------
+    fi, mi = np.nonzero(label >= 0)
+    key = fi.astype(np.int64) * M + label[fi, mi]
+    order = np.lexsort((mi, key))
+    fi, mi, key = fi[order], mi[order], key[order]
+    ci = cam_of[fi, mi]
+    ukey, start = np.unique(key, return_index=True)
+    cnt = np.diff(np.append(start, key.size))
+    # members table (cluster, camera) -> detection, -1 = none, -2 = several
+    members = -np.ones((ukey.size, C), dtype=np.int64)
+    cl = np.repeat(np.arange(ukey.size), cnt)
+    first = np.ones(key.size, dtype=bool)
+    pair = cl * C + ci
+    first[1:] = pair[1:] != pair[:-1]
+    members[cl[first], ci[first]] = mi[first]
+    dup_clusters = np.unique(cl[~first])
+    persons = []                                      # (frame, sort key, member row)
+    clean = np.setdiff1d(np.arange(ukey.size), dup_clusters)
+    for k in clean:
+        persons.append((int(ukey[k] // M), (int(ukey[k] % M), 0), members[k]))
+    if dup_clusters.size:
+        # every combination of every ambiguous cluster, scored in one batch (get_best_comb, step2:610-646)
+        def score_round(groups):
+            combos, owner = [], []
+            for gi, (f, dets) in enumerate(groups):
+                per_cam = [[m for m in dets if cam_of[f, m] == c] or [-1] for c in range(C)]
+                for combo in itertools.product(*per_cam):
+                    combos.append(combo)
+                    owner.append(gi)
+            combos = np.array(combos, dtype=np.int64)
+            owner = np.array(owner)
+            fr = np.array([groups[g][0] for g in owner])
+            has = combos >= 0
+            safe = np.where(has, combos, 0)
+            raw_sel = kp_raw[fr[:, None], safe] * has[..., None, None]
+            und_sel = np.where(has[..., None, None], und[fr[:, None], safe], 0.0)
+            p3d = _ls_persons(cgroup, und_sel, raw_sel[..., 2], thr_kp)
+            err = _combo_rmse(cgroup, raw_sel, p3d, thr_kp)
+            best = []
+            for gi in range(len(groups)):
+                idx = np.nonzero(owner == gi)[0]
+                best.append(combos[idx[int(np.argmin(err[idx]))]])          # first minimum, like np.argmin
+            return best
+        groups = []
+        for k in dup_clusters:
+            f = int(ukey[k] // M)
+            groups.append((f, mi[cl == k].tolist()))
+        best = score_round(groups)
+        left_groups, left_of = [], []
+        for gi, k in enumerate(dup_clusters):
+            f, dets = groups[gi]
+            persons.append((f, (int(ukey[k] % M), 0), best[gi]))
+            rest = sorted(set(dets) - set(int(m) for m in best[gi] if m >= 0))
+            if len(rest) > 1:                                               # step2:653-657
+                left_groups.append((f, rest))
+                left_of.append(k)
+        if left_groups:
+            # a leftover group with one detection per camera is taken as is, otherwise scored again
+            best2 = score_round(left_groups)
+            for (f, rest), k, b in zip(left_groups, left_of, best2):
+                persons.append((f, (int(ukey[k] % M), 1), b))
+    persons = [p for p in persons if (p[2] >= 0).sum() >= 2]                # step2:697-698
+    persons.sort(key=lambda p: (p[0], p[1]))
+    P = len(persons)
+    frame = np.array([p[0] for p in persons], dtype=np.int64)
+    mem = np.array([p[2] for p in persons], dtype=np.int64).reshape(P, C)
+    has = mem >= 0
+    safe = np.where(has, mem, 0)
+    if P:
+        und_sel = np.where(has[..., None, None], und[frame[:, None], safe], 0.0)
+        sc_sel = kp_raw[frame[:, None], safe][..., 2] * has[..., None]
+        p3d = _ls_persons(cgroup, und_sel, sc_sel, thr_kp)
+    else:
+        p3d = np.zeros((0, J, 3))
+    src = mem if bbox_id is None else np.where(has, np.asarray(bbox_id)[frame[:, None], safe], -1)
+    return {"label": label, "frame": frame, "members": mem, "p3d": p3d, "bcomb": np.where(has, src, -1)}
+
+
 class MultiEstimator:
-    """Matching and 3D reconstruction across cameras for a single keyframe — the host logic of
-    step2_crossviewmatching.py:494-713 with every geometric step on the GPU kernels
-    (ray affinity, SVT association, LS triangulation, omnidir reprojection).  Drawing
-    (``show=True``) and the unused spectral initialisation (:577-586) are not reproduced."""
+    """Matching and 3D reconstruction across cameras for a single keyframe: the call shape of
+    step2_crossviewmatching.py:494-713 on ``associate_batch`` with F = 1 (the reference's per-keyframe
+    loop, step2:899-928, is better served by calling ``associate_batch`` once for all keyframes).
+    Drawing (``show=True``) is not reproduced."""
 
     def __init__(self, cfg=None, debug=False):
         self.cfg = cfg
         self.debug = debug
 
     def predict_data(self, info_dict, show=False, plt_id=0, camparam=None, bcomb_prev=None):
-        import itertools
         _need_camparam(camparam)
         if show:
             raise NotImplementedError("predict_data(show=True) draws with matplotlib (step2:648-693)")
-        n_cam = len(info_dict)
-        dimGroup = [0]
-        cnt = 0
-        for cam_id in range(n_cam):
-            cnt += len(info_dict[cam_id][0])
-            dimGroup.append(cnt)
-        dimGroup = np.array(dimGroup)
-        info_list = []
-        for cam_id in range(n_cam):
-            info_list.extend(info_dict[cam_id][0])
-        if not info_list:
+        cg = group_from_camparam(camparam)
+        dets = [d for cam_id in range(len(info_dict)) for d in info_dict[cam_id][0]]
+        if not dets:
             return [], [], []
-        M = len(info_list)
-        n_kp = MODEL_CFG["joint_num"]
-        pose2d = np.array([det["pose2d"] for det in info_list]).reshape(M, n_kp, 2)
-        pose_score = np.array([det["pose2d_raw"] for det in info_list]).reshape(M, n_kp, 3)[..., 2]
-        kp_mat = np.concatenate([pose2d, pose_score[..., np.newaxis]], axis=2)
-        sub2cam = np.zeros(M, dtype=int)
-        for idx in range(len(dimGroup) - 1):
-            sub2cam[dimGroup[idx]:dimGroup[idx + 1]] = idx
-        cid_list = [det["cid"] for det in info_list]
-
-        geo_aff = geometry_affinity2(kp_mat.copy(), dimGroup, self.cfg, camparam=camparam)      # :554
-        cid = np.asarray(cid_list)
-        cid_mat = ((sub2cam[:, None] != sub2cam[None, :]) & (cid[:, None] >= 0) &
-                   (cid[:, None] == cid[None, :])).astype(np.float64)                          # :557-561
-        W = ALPHA_ID * cid_mat + (1 - ALPHA_ID) * geo_aff                                      # :572-575
-        W *= (geo_aff > 0)
-        W = np.nan_to_num(W)
-        match_mat = matchSVT(W, dimGroup, alpha=MODEL_CFG["alpha_SVT"], _lambda=MODEL_CFG["lambda_SVT"],
-                             dual_stochastic_SVT=MODEL_CFG["dual_stochastic_SVT"])              # :589-595
-        col_sums = match_mat.sum(axis=0)                                                       # :598-607
-        matched_cols = np.nonzero(col_sums > 1.9)[0]
-        bin_match = match_mat[:, matched_cols] > 0.9
-        matched_list = [[] for _ in range(bin_match.shape[1])]
-        for sub_idx, row in enumerate(bin_match):
-            if row.sum() != 0:
-                matched_list[row.argmax()].append(sub_idx)
-        matched_list = [np.array(lst) for lst in matched_list]
-
-        def get_best_comb(person_idxs):                                                        # :610-646
-            person_idxs = np.asarray(person_idxs, dtype=int)
-            cam_ids = sub2cam[person_idxs]
-            cam_groups = [person_idxs[np.where(cam_ids == c)].tolist() or [None] for c in range(n_cam)]
-            combos = list(itertools.product(*cam_groups))
-            if len(combos) == 1:
-                return person_idxs
-            errors = []
-            for combo in combos:
-                kp2d = np.zeros((n_cam, n_kp, 3))
-                for c, sub_idx in enumerate(combo):
-                    if sub_idx is not None:
-                        kp2d[c] = info_list[sub_idx]["pose2d_raw"]
-                p3d = calc_3dpose(kp2d, self.cfg, camparam=camparam)
-                derrs = []
-                for c, sub_idx in enumerate(combo):
-                    if sub_idx is None:
-                        continue
-                    raw = np.asarray(info_list[sub_idx]["pose2d_raw"])
-                    ok = raw[:, 2] > THR_KP
-                    derrs.append(raw[ok, :2] - reproject(c, p3d, camparam=camparam)[ok])
-                errors.append(np.sqrt((np.vstack(derrs) ** 2).mean()) if derrs else np.inf)
-            best = combos[int(np.argmin(errors))]
-            return np.array([i for i in best if i is not None], dtype=int)
-
-        refined = []
-        for person in matched_list:                                                            # :649-657
-            best = get_best_comb(person)
-            refined.append(best)
-            leftover = set(person.tolist()) - set(best.tolist())
-            if len(leftover) > 1:
-                refined.append(get_best_comb(np.array(list(leftover), dtype=int)))
-        P3d_list, matched_list2, bcomb_list = [], [], []
-        for person_idxs in refined:                                                            # :696-713
-            if person_idxs.shape[0] < 2:
-                continue
-            kp2d = np.zeros((n_cam, n_kp, 3))
-            for sub_idx in person_idxs:
-                kp2d[sub2cam[sub_idx]] = info_list[sub_idx]["pose2d_raw"]
-            P3d_list.append(calc_3dpose(kp2d, self.cfg, camparam=camparam))
-            bcomb = -np.ones(n_cam, dtype=int)
-            for sub_idx in person_idxs:
-                bcomb[sub2cam[sub_idx]] = info_list[sub_idx]["bbox_id"][1]
-            matched_list2.append(person_idxs)
-            bcomb_list.append(bcomb)
-        return matched_list2, P3d_list, bcomb_list
+        J = MODEL_CFG["joint_num"]
+        dim = np.cumsum([0] + [len(info_dict[c][0]) for c in range(len(info_dict))]).astype(np.int32)[None]
+        kp_raw = np.array([d["pose2d_raw"] for d in dets], dtype=np.float64).reshape(1, len(dets), J, 3)
+        cid = np.array([d["cid"] for d in dets], dtype=np.int32)[None]
+        bbox = np.array([d["bbox_id"][1] for d in dets], dtype=np.int64)[None]
+        res = associate_batch(cg, kp_raw, dim, cid, bbox, thr_kp=THR_KP, alpha_id=ALPHA_ID,
+                              alpha_svt=MODEL_CFG["alpha_SVT"], lambda_svt=MODEL_CFG["lambda_SVT"])
+        matched = [row[row >= 0] for row in res["members"]]
+        return matched, list(res["p3d"]), list(res["bcomb"])
 
 
 # ------------------------------------------------------------------------------------------

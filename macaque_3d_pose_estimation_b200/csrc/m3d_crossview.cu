@@ -288,8 +288,10 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
               ab += x.x * y.x;
               ab += x.y * y.y;
             }
-            for (int off = g >> 1; off > 0; off >>= 1) ab += __shfl_xor_sync(gmask, ab, off, 32);
+            // read the running norms BEFORE the group's shuffles: lane sub == 0 overwrites them below,
+            // and only the shuffle keeps it from running ahead of a lane that has not read them yet
             double aa = nrm[p], bb = nrm[q];
+            for (int off = g >> 1; off > 0; off >>= 1) ab += __shfl_xor_sync(gmask, ab, off, 32);
             aa = aa > 0.0 ? aa : 0.0;
             bb = bb > 0.0 ? bb : 0.0;
             // rotate when |ab| > 1e-15 sqrt(aa bb); MUFU-seeded reciprocal / sqrt (m3d_math.cuh)
@@ -398,7 +400,93 @@ k_match_svt(const double* __restrict__ Wall, const int32_t* __restrict__ dim, in
   }
 }
 
+// W = alpha_id * [same identity, different cameras] + (1 - alpha_id) * aff, zero where aff <= 0 or NaN
+// (MultiEstimator.predict_data, step2_crossviewmatching.py:557-575); thread = matrix entry
+__global__ void __launch_bounds__(256)
+k_assoc_weights(const double* __restrict__ aff, const int32_t* __restrict__ cid, const int32_t* __restrict__ dim,
+                int F, int M, int C, double alpha_id, double* __restrict__ W) {
+  const int64_t n = (int64_t)F * M * M;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(t / ((int64_t)M * M));
+    const int r = (int)(t % ((int64_t)M * M));
+    const int i = r / M, j = r % M;
+    const int32_t* dg = dim + (int64_t)f * (C + 1);
+    const int nd = dg[C];
+    double w = 0.0;
+    if (i < nd && j < nd) {
+      const double a = aff[t];
+      if (a > 0.0) {  // also drops NaN (np.nan_to_num after the mask, :574-575)
+        int ci = 0, cj = 0;
+        for (int c = 1; c <= C; ++c) {
+          ci += (i >= dg[c]);
+          cj += (j >= dg[c]);
+        }
+        const int32_t idi = cid[(int64_t)f * M + i], idj = cid[(int64_t)f * M + j];
+        const double same = (ci != cj && idi >= 0 && idi == idj) ? 1.0 : 0.0;
+        w = alpha_id * same + (1.0 - alpha_id) * a;
+      }
+    }
+    W[t] = w;
+  }
+}
+
+// Person clusters of a match matrix (step2_crossviewmatching.py:598-607): columns whose sum is > 1.9
+// are persons; a detection belongs to the first such column it is matched to.  One warp per frame.
+__global__ void __launch_bounds__(128)
+k_match_clusters(const uint8_t* __restrict__ match, const int32_t* __restrict__ dim, int F, int M, int C,
+                 int32_t* __restrict__ label) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < F; f += warps) {
+    const int nd = dim[(int64_t)f * (C + 1) + C];
+    const uint8_t* m = match + (int64_t)f * M * M;
+    // person columns as bit masks (M <= 128): lane handles columns lane, lane + 32, ...
+    uint32_t is_person[4] = {0, 0, 0, 0};
+    for (int j = lane; j < nd; j += 32) {
+      int sum = 0;
+      for (int i = 0; i < nd; ++i) sum += m[(int64_t)i * M + j];
+      if (sum >= 2) is_person[j >> 5] = 1u;  // lane-local flag for column j = 32 * (j >> 5) + lane
+    }
+    uint32_t pm[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) pm[w] = __ballot_sync(0xffffffffu, is_person[w] != 0);
+    for (int i = lane; i < M; i += 32) {
+      int lab = -1;
+      if (i < nd) {
+        for (int j = 0; j < nd && lab < 0; ++j)
+          if (((pm[j >> 5] >> (j & 31)) & 1u) && m[(int64_t)i * M + j]) lab = j;
+      }
+      label[(int64_t)f * M + i] = lab;
+    }
+  }
+}
+
 extern "C" {
+
+int m3d_association_weights(const double* aff, const int32_t* cid, const int32_t* dim, int32_t F, int32_t M,
+                            int32_t C, double alpha_id, double* W, int32_t device, void* stream) {
+  if (F < 0 || M < 0 || C < 0 || C > M3D_MAX_CAMS) return m3d_fail(M3D_ERR_INVALID, "m3d_association_weights: bad size");
+  if (F == 0 || M == 0) return M3D_OK;
+  if (!aff || !cid || !dim || !W) return m3d_fail(M3D_ERR_INVALID, "m3d_association_weights: NULL buffer");
+  M3dDeviceGuard guard(device);
+  int64_t blocks = ((int64_t)F * M * M + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_assoc_weights<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(aff, cid, dim, F, M, C, alpha_id, W);
+  return m3d_check_launch("k_assoc_weights");
+}
+
+int m3d_match_clusters(const uint8_t* match, const int32_t* dim, int32_t F, int32_t M, int32_t C, int32_t* label,
+                       int32_t device, void* stream) {
+  if (F < 0 || M < 0 || C < 0 || C > M3D_MAX_CAMS || M > M3D_MAX_DETS)
+    return m3d_fail(M3D_ERR_INVALID, "m3d_match_clusters: bad size");
+  if (F == 0 || M == 0) return M3D_OK;
+  if (!match || !dim || !label) return m3d_fail(M3D_ERR_INVALID, "m3d_match_clusters: NULL buffer");
+  M3dDeviceGuard guard(device);
+  int blocks = (F + 3) / 4;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_match_clusters<<<blocks, 128, 0, (cudaStream_t)stream>>>(match, dim, F, M, C, label);
+  return m3d_check_launch("k_match_clusters");
+}
 
 int m3d_ray_affinity(const m3d_rig* rig, const double* kp, const int32_t* dim, int32_t F, int32_t M,
                      int32_t J, double thr_kp, double* aff, double* dist, void* stream) {

@@ -120,3 +120,90 @@ def triangulate_ls(cams, xy_undist, frame_use):
         A = np.vstack(rows)
         out[i] = -(np.linalg.pinv(A[:, :3]) @ A[:, 3])
     return out
+
+
+def associate_frame(cams, kp_raw, dimGroup, cid, bbox_id, thr_kp=0.1, alpha_id=0.2, alpha_svt=0.5, lam=50.0):
+    """MultiEstimator.predict_data for one keyframe in the reference's own loop structure
+    (step2_crossviewmatching.py:502-713) with the camera model taken from ``cams`` (the reference hard-wires
+    cv2.omnidir there, which this container cannot execute): affinity :554, identity term :557-575,
+    matchSVT :589-595, clusters :598-607, get_best_comb :610-646, leftovers :649-657, 3D poses :696-713.
+    kp_raw (M,J,3) raw pixels + score.  Returns (matched_list, P3d_list, bcomb_list)."""
+    import itertools
+    kp_raw = np.asarray(kp_raw, dtype=np.float64)
+    M, J, _ = kp_raw.shape
+    C = len(cams)
+    dimGroup = np.asarray(dimGroup)
+    sub2cam = np.zeros(M, dtype=int)
+    for idx in range(C):
+        sub2cam[dimGroup[idx]:dimGroup[idx + 1]] = idx
+    und = np.stack([cams[sub2cam[i]].undistort(kp_raw[i, :, :2]) for i in range(M)]) if M else np.zeros((0, J, 2))
+    kp_mat = np.concatenate([und, kp_raw[:, :, 2:3]], axis=2)
+    geo = geometry_affinity(cams, kp_mat, dimGroup, thr_kp)
+    cid = np.asarray(cid)
+    cid_mat = np.zeros((M, M))
+    for i in range(M):
+        for j in range(M):
+            if sub2cam[i] != sub2cam[j] and cid[i] >= 0 and cid[i] == cid[j]:
+                cid_mat[i, j] = 1
+    W = alpha_id * cid_mat + (1 - alpha_id) * geo
+    W *= (geo > 0)
+    W = np.nan_to_num(W)
+    match_mat = match_svt(W, dimGroup, alpha=alpha_svt, lam=lam)
+    bin_match = match_mat[:, np.nonzero(np.sum(match_mat, axis=0) > 1.9)[0]] > 0.9
+    bin_match = bin_match.reshape(M, -1)
+    matched_list = [[] for _ in range(bin_match.shape[1])]
+    for sub_imgid, row in enumerate(bin_match):
+        if row.sum() != 0:
+            matched_list[np.argmax(row)].append(sub_imgid)
+    # (an empty cluster — all rows of a person column claimed by earlier columns — makes the reference's
+    # float-typed empty index array raise; it carries no person either way)
+    matched_list = [np.array(x, dtype=int) for x in matched_list if len(x)]
+
+    def pose3d(kp2d):                                            # calc_3dpose, step2:436-461
+        u = np.stack([cams[c].undistort(kp2d[c, :, :2]) for c in range(C)])
+        use = ~(np.isnan(kp2d[:, :, 0]) | (kp2d[:, :, 2] < thr_kp))
+        return triangulate_ls(cams, np.nan_to_num(u), use.T)
+
+    def get_best_comb(person):
+        cam_list = sub2cam[person]
+        groups = [np.array(person)[np.argwhere(cam_list == c).ravel()].tolist() or [None] for c in range(C)]
+        combs = list(itertools.product(*groups))
+        if len(combs) == 1:
+            return np.array(person)
+        errs = []
+        for comb in combs:
+            kp2d = np.zeros((C, J, 3))
+            for c, i in enumerate(comb):
+                if i is not None:
+                    kp2d[c] = kp_raw[i]
+            p3d = pose3d(kp2d)
+            d = []
+            for c, i in enumerate(comb):
+                if i is not None:
+                    keep = kp_raw[i][:, 2] > thr_kp
+                    d.append(kp_raw[i][keep, :2] - cams[c].project(p3d)[keep])
+            errs.append(np.sqrt(np.mean(np.concatenate(d, axis=0) ** 2)))
+        best = combs[int(np.argmin(errs))]
+        return np.array([i for i in best if i is not None])
+
+    refined = []
+    for person in matched_list:
+        b = get_best_comb(person)
+        refined.append(b)
+        rest = set(person.tolist()) - set(b.tolist())
+        if len(rest) > 1:
+            refined.append(get_best_comb(np.array(list(rest))))
+    out_m, out_p, out_b = [], [], []
+    for person in refined:
+        if person.shape[0] < 2:
+            continue
+        kp2d = np.zeros((C, J, 3))
+        for i in person:
+            kp2d[sub2cam[i]] = kp_raw[i]
+        out_p.append(pose3d(kp2d))
+        bc = -np.ones(C, dtype=int)
+        for i in person:
+            bc[sub2cam[i]] = bbox_id[i]
+        out_m.append(person)
+        out_b.append(bc)
+    return out_m, out_p, out_b

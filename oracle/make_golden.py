@@ -223,6 +223,63 @@ def case_crossview(ref, name, n_frames, seed, drop=0.0):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
 
 
+def case_svt(ref, name, n_frames, seed, drop=0.15, p_cid=0.7, p_cid_wrong=0.1, noise=4e-4):
+    """matchSVT (step2_crossviewmatching.py:130-216) alone on many keyframes: ragged detection counts,
+    the identity term of predict_data switched on (W = 0.2 cid + 0.8 aff, :557-575, with some wrong and
+    some missing identities), 2D noise levels from clean to heavy so that part of the frames do NOT
+    converge to a clean block structure.  The affinity comes from the numpy oracle (pinned against the
+    reference by the crossview_* goldens); the match matrices are the executed reference's."""
+    from src.pipeline import step2_crossviewmatching as s2
+    from oracle import crossview as ocv
+    from oracle import fixtures
+    C, A, J = 8, 6, 17
+    cams = synth.make_rig(C, "pinhole", seed=seed)
+    specs = fixtures.cams_from_dicts(cams)
+    rng = np.random.default_rng(seed + 5)
+    from oracle import camera_math as cm
+    P = [np.hstack([cm.rodrigues(np.array(d["rotation"])), np.array(d["translation"]).reshape(3, 1)]) for d in cams]
+    X = synth.make_tracks(n_frames, A, seed=seed)
+    Ws, dims, matches, iters = [], [], [], []
+    t0 = time.time()
+    for f in range(n_frames):
+        nz = noise * (1.0 if f % 4 else 6.0) * (1.0 + 3.0 * rng.random())     # every 4th frame is much noisier
+        kps, dim, owner = [], [0], []
+        for c in range(C):
+            for a in range(A):
+                if rng.random() < drop:
+                    continue
+                Xc = X[f, a] @ P[c][:, :3].T + P[c][:, 3]
+                xy = Xc[:, :2] / Xc[:, 2:3] + rng.normal(0, nz, size=(J, 2))
+                sc = rng.uniform(0.3, 1.0, size=J)
+                sc[rng.random(J) < 0.1] = 0.0
+                kps.append(np.concatenate([xy, sc[:, None]], axis=1))
+                owner.append(a)
+            dim.append(len(kps))
+        kp, dimGroup, owner = np.array(kps), np.array(dim), np.array(owner)
+        M = kp.shape[0]
+        aff = ocv.geometry_affinity(specs, kp, dimGroup)
+        cid = np.where(rng.random(M) < p_cid, owner, -1)
+        wrong = rng.random(M) < p_cid_wrong
+        cid[wrong] = rng.integers(0, A, size=int(wrong.sum()))
+        sub2cam = np.searchsorted(dimGroup, np.arange(M), side="right") - 1
+        cid_mat = ((sub2cam[:, None] != sub2cam[None, :]) & (cid[:, None] >= 0) & (cid[:, None] == cid[None, :])).astype(float)
+        W = 0.2 * cid_mat + 0.8 * aff
+        W *= (aff > 0)
+        W = np.nan_to_num(W)
+        match = s2.matchSVT(W.copy(), dimGroup, alpha=0.5, _lambda=50, dual_stochastic_SVT=False)
+        Wp = np.zeros((A * C, A * C))
+        Wp[:M, :M] = W
+        mp = np.zeros((A * C, A * C), dtype=np.uint8)
+        mp[:M, :M] = match
+        Ws.append(Wp)
+        dims.append(dimGroup)
+        matches.append(mp)
+        if f % 20 == 0:
+            print(name, "frame", f, "M=%d  %.0f s" % (M, time.time() - t0), flush=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rig_arrays(cams), W=np.array(Ws), dim=np.array(dims),
+                        match=np.array(matches), n_frames=np.array(n_frames))
+
+
 def case_possible(ref, name, n_cams, n_frames, seed, n_possible=2, min_cams=2, p_swap=0.3, p_missing=0.2):
     """CameraGroup.triangulate_possible with P candidates per camera (cameras.py:639-724): the
     second candidate is a distractor (N(0, 40 px) away) or missing; in 30 % of the (camera, point)
@@ -386,6 +443,7 @@ def main():
         "viterbi_p1": lambda: case_viterbi("viterbi_p1", 400, 6, 1, S + 31),
         "viterbi_p2": lambda: case_viterbi("viterbi_p2", 150, 4, 2, S + 32),
         "viterbi_p1_nb4": lambda: case_viterbi("viterbi_p1_nb4", 120, 3, 1, S + 33, n_back=4, offset_threshold=10),
+        "svt_ragged_f240": lambda: case_svt(ref, "svt_ragged_f240", 240, S + 61),
         "optim_c8_n2": lambda: case_optim(ref, "optim_c8_n2", 8, 48, S + 51),
         "optim_c4_n1_huber": lambda: case_optim(ref, "optim_c4_n1_huber", 4, 30, S + 52, n_deriv=1, reproj_loss="huber",
                                                 with_scores=True),

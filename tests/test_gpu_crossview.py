@@ -75,6 +75,90 @@ def test_gpu_crossview_golden(name):
         assert abs(int(its[f]) - it_ref) <= 2
 
 
+def test_gpu_match_svt_240_reference_frames():
+    """matchSVT bit-exact on 240 keyframes executed by the reference (ragged detection counts, identity
+    term on, every 4th frame with heavy 2D noise: frames that do not settle into clean blocks)."""
+    g, _ = fixtures.load_golden("svt_ragged_f240")
+    W, dim, ref = g["W"], g["dim"].astype(np.int32), g["match"]
+    got, its = cv.match_svt_batch(W, dim, dim.shape[1] - 1, alpha=0.5, _lambda=50.0, return_iters=True)
+    bad = [f for f in range(W.shape[0]) if not np.array_equal(got[f], ref[f])]
+    assert not bad, "match matrices differ from the reference in frames %s" % bad[:10]
+    assert int(its.max()) > int(np.median(its)) + 5            # the set does contain slow frames
+
+
+def _association_case(seed, F, model="pinhole", dup=0.08, drop=0.12, noise=0.4):
+    from macaque_3d_pose_estimation_b200 import synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+    C, A, J = 8, 6, 17
+    dicts = synth.make_rig(C, model, seed=seed)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    rng = np.random.default_rng(seed)
+    X = synth.make_tracks(F, A, seed=seed) * np.array([0.6, 0.6, 0.5])
+    M = C * (A + 2)
+    kp = np.zeros((F, M, J, 3))
+    dim = np.zeros((F, C + 1), dtype=np.int32)
+    cid = -np.ones((F, M), dtype=np.int32)
+    bbox = -np.ones((F, M), dtype=np.int64)
+    owner = -np.ones((F, M), dtype=np.int64)
+    for f in range(F):
+        m = 0
+        for c in range(C):
+            for a in rng.permutation(A):
+                if rng.random() < drop:
+                    continue
+                reps = 2 if rng.random() < dup else 1         # the detector fires twice on one animal
+                for r in range(reps):
+                    if m >= dim[f, c] + A + 2:
+                        break
+                    raw = cams[c].project(X[f, a]) + rng.normal(0, noise * (1 + 4 * r), size=(J, 2))
+                    sc = rng.uniform(0.3, 1.0, size=J)
+                    sc[rng.random(J) < 0.1] = 0.0
+                    kp[f, m] = np.concatenate([raw, sc[:, None]], axis=1)
+                    cid[f, m] = a if rng.random() < 0.6 else -1
+                    bbox[f, m] = 100 * c + m
+                    owner[f, m] = a
+                    m += 1
+            dim[f, c + 1] = m
+    return cg, cams, X, kp, dim, cid, bbox, owner
+
+
+@pytest.mark.parametrize("seed,model", [(51, "pinhole"), (52, "fisheye")])
+def test_gpu_associate_batch_equals_per_frame_oracle(seed, model):
+    """associate_batch (all keyframes per launch) against the loop-faithful restatement of
+    MultiEstimator.predict_data (oracle/crossview.py associate_frame) frame by frame: same persons, same
+    members (incl. the duplicate-detection combinations of get_best_comb), same 3D poses."""
+    F = 24
+    cg, cams, X, kp, dim, cid, bbox, owner = _association_case(seed, F, model)
+    res = cv.associate_batch(cg, kp, dim, cid, bbox)
+    n_dup_frames = 0
+    for f in range(F):
+        n = int(dim[f, -1])
+        m_ref, p_ref, b_ref = ocv.associate_frame(cams, kp[f, :n], dim[f], cid[f, :n], bbox[f, :n])
+        sel = np.nonzero(res["frame"] == f)[0]
+        assert len(sel) == len(m_ref), "frame %d: %d persons, reference %d" % (f, len(sel), len(m_ref))
+        for k, (mr, pr, br) in zip(sel, zip(m_ref, p_ref, b_ref)):
+            mine = res["members"][k]
+            assert sorted(mine[mine >= 0].tolist()) == sorted(np.asarray(mr).tolist())
+            assert np.array_equal(res["bcomb"][k], br)
+            assert np.array_equal(np.isnan(res["p3d"][k]), np.isnan(pr))
+            assert np.nanmax(np.abs(res["p3d"][k] - pr), initial=0.0) <= 1e-6
+        lab = res["label"][f, :n]
+        for c in range(8):
+            seg = lab[dim[f, c]:dim[f, c + 1]]
+            seg = seg[seg >= 0]
+            n_dup_frames += int(len(seg) != len(set(seg.tolist())))
+    assert n_dup_frames > 0, "no duplicate-detection cluster in the test data"
+    # the persons are the animals
+    good = 0
+    for k in range(len(res["frame"])):
+        f = int(res["frame"][k])
+        mem = res["members"][k]
+        own = owner[f, mem[mem >= 0]]
+        good += int(len(set(own.tolist())) == 1 and np.nanmax(np.abs(res["p3d"][k] - X[f, own[0]])) < 25.0)
+    assert good >= 0.9 * len(res["frame"])
+
+
 def test_gpu_keyframe_association_recovers_animals():
     """MultiEstimator.predict_data (step2:502-713) on a synthetic omnidir rig, 6 animals x 8 views:
     the clusters must be the animals and the 3D poses the ground truth.  (The reference's own
