@@ -304,6 +304,64 @@ def optim_line(cx, args):
     return out
 
 
+def cfg4_line(cx, args):
+    """BASELINE config 4: cross-view affinity + SVT association + triangulation, 6 macaques x 8 views,
+    --cfg4-frames keyframes (default 100k) through crossview.associate_batch in chunks of 10k keyframes
+    (host arrays in, host arrays out)."""
+    import numpy as np
+    from macaque_3d_pose_estimation_b200 import crossview, synth
+    out = {}
+    try:
+        C, A, J = args.cameras, 6, 17
+        F = args.cfg4_frames
+        rng = np.random.default_rng(404)
+        X = synth.make_tracks(F, A, seed=404) * np.array([0.6, 0.6, 0.5])              # (F, A, J, 3)
+        proj = cx.cg.project(X.reshape(-1, 3)).reshape(C, F, A, J, 2)
+        M = C * A
+        kp = np.empty((F, M, J, 3))
+        kp[..., :2] = proj.transpose(1, 0, 2, 3, 4).reshape(F, M, J, 2) + rng.normal(0, 0.4, size=(F, M, J, 2))
+        sc = rng.uniform(0.3, 1.0, size=(F, M, J))
+        sc[rng.random((F, M, J)) < 0.1] = 0.0
+        kp[..., 2] = sc
+        dim = np.tile(np.arange(C + 1, dtype=np.int32) * A, (F, 1))
+        owner = np.tile(np.tile(np.arange(A), C), (F, 1))
+        cid = np.where(rng.random((F, M)) < 0.6, owner, -1).astype(np.int32)
+        chunk = 10000
+        crossview.associate_batch(cx.cg, kp[:2000], dim[:2000], cid[:2000])              # warm-up
+        t0 = time.perf_counter()
+        n_person, ok = 0, 0
+        for a in range(0, F, chunk):
+            res = crossview.associate_batch(cx.cg, kp[a:a + chunk], dim[a:a + chunk], cid[a:a + chunk])
+            n_person += len(res["frame"])
+            mem = res["members"]
+            own = np.where(mem >= 0, owner[0][np.where(mem >= 0, mem, 0)], -1)
+            first = own.max(axis=1)
+            ok += int(((own == first[:, None]) | (own < 0)).all(axis=1).sum())
+        dt = time.perf_counter() - t0
+        out = {"workload": "cfg4: cross-view ray affinity + SVT association + LS triangulation, 6 macaques x %d "
+                           "views (M = %d detections per keyframe), %d keyframes" % (C, M, F),
+               "value": F / dt, "unit": "keyframes/s (one GPU, host arrays in and out)", "seconds": dt,
+               "joint_instances_per_s": F * A * J / dt, "persons_found_per_frame": n_person / F,
+               "pure_clusters_fraction": ok / max(1, n_person)}
+        if not args.no_cpu:
+            from oracle import crossview as ocv
+            from oracle import fixtures
+            cams = fixtures.cams_from_dicts(synth.make_rig(C, "pinhole", seed=20261018 + 2))
+            nf = 6
+            t0 = time.perf_counter()
+            for f in range(nf):
+                ocv.associate_frame(cams, kp[f], dim[f], cid[f], np.arange(M))
+            dtc = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nf / dtc, "unit": "keyframes/s", "cores": 1, "kind": "port",
+                                   "sample": "%d keyframes through the loop-faithful restatement of "
+                                             "MultiEstimator.predict_data (oracle/crossview.py associate_frame; the "
+                                             "reference's own affinity loop is ~100x slower than this numpy form: "
+                                             "0.86 s + 1.1 s per keyframe measured, SURVEY.md 8a)" % nf}
+    except Exception as ex:  # pragma: no cover
+        out = {"error": str(ex)[:300]}
+    return out
+
+
 def config_dict(workload, C, frames_per_gpu, n_gpus, extra=None):
     d = {"workload": NAMES[workload] % C, "cameras": C, "camera_model": "pinhole(5 coeff)",
          "joint_instances_per_gpu": int(frames_per_gpu * ANIMALS * JOINTS), "frames_per_gpu": int(frames_per_gpu),
@@ -723,7 +781,7 @@ def run_gpu(args):
         warm = torch.zeros((cx.world * 8,), dtype=torch.float64, device=cx.device)
         dist.all_reduce(warm)                     # communicator set-up outside every timing
     cx.lib = _lib.require_gpu()
-    cx.cg = CameraGroup.from_dicts(synth.make_rig(args.cameras, "pinhole", seed=20261018 + 2))
+    cx.cg = CameraGroup.from_dicts(synth.make_rig(args.cameras, "pinhole", seed=args.rig_seed))
     cx.cg.device = cx.local
     cx.rig = cx.cg._rig(cx.local)
     cx.stream = torch.cuda.current_stream(cx.device)
@@ -772,6 +830,7 @@ def run_gpu(args):
     line.update(head["extra"])
     if cx.world == 1 and not args.only:
         line["optim_points"] = optim_line(cx, args)
+        line["cfg4"] = cfg4_line(cx, args)
     if second is not None:
         key = "cfg2" if other == "dlt" else "cfg3"
         sec = {k: second[k] for k in ("value", "ms_per_step", "gpu_launches", "config", "roofline", "e2e") if k in second}
@@ -799,6 +858,8 @@ def main():
     ap.add_argument("--e2e-points", type=int, default=20000000,
                     help="joint-instances per GPU of the e2e run (the same at every N)")
     ap.add_argument("--cameras", type=int, default=8, help="cameras of the synthetic ring rig (BASELINE: 8; config 5: 16)")
+    ap.add_argument("--cfg4-frames", type=int, default=100000, help="keyframes of the config-4 association line")
+    ap.add_argument("--rig-seed", type=int, default=20261018 + 2, help="seed of the synthetic ring rig")
     ap.add_argument("--only", action="store_true", help="measure the headline workload only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -438,7 +438,11 @@ int m3d_rig_create(const m3d_cam* cams, int32_t n_cams, int32_t device, m3d_rig*
     }
   }
   build_cert(rig->dev, &rig->cert);
-  rig->cert_all = n_cams >= 2 && rig->cert.ok_mask == (1 << n_cams) - 1 &&
+  // pruned search when at most one camera lacks a certificate (an uncertified camera simply never
+  // takes part in a certified-bad pair: the search stays exact, its subsets are solved)
+  int n_cert = 0;
+  for (int c = 0; c < n_cams; ++c) n_cert += (rig->cert.ok_mask >> c) & 1;
+  rig->cert_all = n_cams >= 2 && n_cert >= n_cams - 1 && n_cert >= 2 &&
                   (rig->dev.flags & (RIG_HAS_RATIONAL | RIG_HAS_PRISM)) == 0;
   *out = rig;
   return M3D_OK;

@@ -183,7 +183,7 @@ def test_gpu_pruned_equals_exhaustive_and_oracle(C, seed, min_cams, n_frames):
     assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]) and np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2], equal_nan=True)
     assert np.nanmax(np.abs(a[3] - b[3])) <= 1e-8
-    if mask == (1 << C) - 1:                                   # the pruned kernel really ran in mode 0
+    if bin(mask).count("1") >= max(2, C - 1):                  # the pruned kernel really ran in mode 0
         n_or = min(p2d.shape[1], 3400 if C <= 8 else (170 if C <= 12 else 24))   # the oracle solves 2^C subsets per point
         ref = og.triangulate_ransac(cams, p2d[:, :n_or], min_cams=min_cams, return_stats=True)
         assert np.array_equal(ref[4], a[4][:n_or]) and np.array_equal(ref[5], a[5][:n_or])
