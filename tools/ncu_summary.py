@@ -8,8 +8,15 @@ import subprocess
 import sys
 
 
+FILTER = []
+for _a in sys.argv:
+    if _a.startswith("--kernel="):
+        FILTER = ["-k", "regex:" + _a[len("--kernel="):]]
+sys.argv = [a for a in sys.argv if not a.startswith("--kernel=")]
+
+
 def page(rep, which, extra=()):
-    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"] + list(extra),
+    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"] + FILTER + list(extra),
                          capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
