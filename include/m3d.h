@@ -153,7 +153,7 @@ int m3d_triangulate_ransac(const m3d_rig* rig, const double* xy_dev, int64_t N,
  * offering its valid candidates (ascending) and then "none"; same skip / accept / stop rules
  * as above.  xy_dev (C,N,P,2) raw pixels (NaN x = no candidate); picked_dev (C,N,P) u8;
  * xy_picked_dev (C,N,2) the chosen candidates; index_dev (N) i32 position of the accepted
- * combination in product order, -1 when none; neval_dev (N) i32.  Limit: C * P <= 32.
+ * combination in product order, -1 when none; neval_dev (N) i32.  Limits: C * P <= 32, P <= 15.
  * (The reference only ever calls this with P == 1, which is m3d_triangulate_ransac.) */
 int m3d_triangulate_possible(const m3d_rig* rig, const double* xy_dev, int64_t N, int32_t P,
                              int32_t undistort, int32_t min_cams, double threshold,
@@ -183,6 +183,18 @@ int m3d_triangulate_ransac_host_f32(const m3d_rig* rig, const float* xy_host, in
                                     double init_best, double* p3d_host, uint8_t* picked_host,
                                     float* xy_picked_host, double* err_host, int32_t* subset_host,
                                     int32_t* neval_host);
+/* The same pipelines on a SPAN of the arrays: every array is laid out for N_total points, the call
+ * processes points [first, first + count) and touches nothing else.  Rigs of the same cameras on
+ * different GPUs, each called from its own thread on a disjoint span, spread one host array over all
+ * GPUs of the box in ONE process (CameraGroup does this for large numpy inputs). */
+int m3d_triangulate_error_host_span(const m3d_rig* rig, const double* xy_host, int64_t N_total,
+                                    int64_t first, int64_t count, int32_t undistort,
+                                    double* p3d_host, double* err_host);
+int m3d_triangulate_ransac_host_span(const m3d_rig* rig, const double* xy_host, int64_t N_total,
+                                     int64_t first, int64_t count, int32_t undistort,
+                                     int32_t min_cams, double threshold, double init_best,
+                                     double* p3d_host, uint8_t* picked_host, double* xy_picked_host,
+                                     double* err_host, int32_t* subset_host, int32_t* neval_host);
 /* cudaHostRegister / cudaHostUnregister for caller-owned numpy buffers. */
 int m3d_host_register(void* ptr, int64_t bytes);
 int m3d_host_unregister(void* ptr);

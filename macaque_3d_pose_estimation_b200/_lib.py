@@ -63,6 +63,8 @@ SIGNATURES = {
     "m3d_triangulate_ransac_host": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "m3d_triangulate_error_host_f32": (ctypes.c_int, [_P, _P, _L, _I, _P, _P]),
     "m3d_triangulate_ransac_host_f32": (ctypes.c_int, [_P, _P, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
+    "m3d_triangulate_error_host_span": (ctypes.c_int, [_P, _P, _L, _L, _L, _I, _P, _P]),
+    "m3d_triangulate_ransac_host_span": (ctypes.c_int, [_P, _P, _L, _L, _L, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "m3d_host_register": (ctypes.c_int, [_P, _L]),
     "m3d_host_unregister": (ctypes.c_int, [_P]),
     "m3d_ray_affinity": (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _D, _P, _P, _P]),

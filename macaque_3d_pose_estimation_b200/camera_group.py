@@ -32,10 +32,47 @@ class CameraGroup:
 
     def _rig(self, device=None):
         device = self._dev() if device is None else device
-        key = (device, tuple(cam._fingerprint() for cam in self.cameras))
-        if self._rig_cache is None or self._rig_cache[0] != key:
-            self._rig_cache = (key, _RigHandle(self.cameras, device))
-        return self._rig_cache[1]
+        fp = tuple(cam._fingerprint() for cam in self.cameras)
+        if self._rig_cache is None or self._rig_cache[0] != fp:
+            self._rig_cache = (fp, {})
+        rigs = self._rig_cache[1]
+        if device not in rigs:
+            rigs[device] = _RigHandle(self.cameras, device)
+        return rigs[device]
+
+    # numpy inputs of at least this many joint-instances are spread over all visible GPUs (one
+    # process, one thread per GPU, each streaming its own span of the caller's arrays); set
+    # ``device`` on the group to pin it to one GPU
+    MULTI_GPU_MIN_POINTS = 4000000
+
+    def _host_devices(self, n):
+        if self.device is not None or n < self.MULTI_GPU_MIN_POINTS or torch is None:
+            return None
+        k = torch.cuda.device_count()
+        return list(range(k)) if k > 1 else None
+
+    def _host_spans(self, devices, n, call):
+        """Run ``call(rig, first, count)`` for one contiguous span per device, concurrently (ctypes
+        releases the GIL for the duration of the C call)."""
+        import threading
+        k = len(devices)
+        bounds = [n * i // k for i in range(k + 1)]
+        errs = []
+
+        def work(dev, a, b):
+            try:
+                call(self._rig(dev), a, b - a)
+            except Exception as e:  # noqa: BLE001 - re-raised below
+                errs.append(e)
+        rigs = [self._rig(d) for d in devices]            # create the handles in this thread
+        ths = [threading.Thread(target=work, args=(d, bounds[i], bounds[i + 1])) for i, d in enumerate(devices)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        del rigs
+        if errs:
+            raise errs[0]
 
     def subset_cameras(self, indices):
         """New group over deep copies of the selected cameras (the reference copies as well)."""
@@ -154,6 +191,13 @@ class CameraGroup:
             src = np.ascontiguousarray(points, dtype=np.float64)
             p3d = np.empty((n, 3))
             err = np.empty(n) if with_err else None
+            devs = self._host_devices(n)
+            if devs:
+                flag = self._undistort_flag(undistort)
+                self._host_spans(devs, n, lambda r, a, cnt: _lib.check(r._lib.m3d_triangulate_error_host_span(
+                    r.handle, _np_ptr(src), n, a, cnt, flag, _np_ptr(p3d), _np_ptr(err)),
+                    "m3d_triangulate_error_host_span"))
+                return p3d, err
             _lib.check(rig._lib.m3d_triangulate_error_host(rig.handle, _np_ptr(src), n, self._undistort_flag(undistort),
                                                            _np_ptr(p3d), _np_ptr(err)),
                        "m3d_triangulate_error_host")
@@ -218,6 +262,14 @@ class CameraGroup:
             err = np.empty(n)
             sub = np.empty(n, dtype=np.int32)
             nev = np.empty(n, dtype=np.int32)
+            devs = self._host_devices(n)
+            if devs:
+                self._host_spans(devs, n, lambda r, a, cnt: _lib.check(r._lib.m3d_triangulate_ransac_host_span(
+                    r.handle, _np_ptr(src), n, a, cnt, int(bool(undistort)), int(min_cams), float(threshold),
+                    float(init_best), _np_ptr(p3d), _np_ptr(picked), _np_ptr(xyp), _np_ptr(err), _np_ptr(sub),
+                    _np_ptr(nev)), "m3d_triangulate_ransac_host_span"))
+                res = (p3d, picked.view(np.bool_), xyp, err)
+                return res + (sub, nev) if return_stats else res
             _lib.check(rig._lib.m3d_triangulate_ransac_host(
                 rig.handle, _np_ptr(src), n, int(bool(undistort)), int(min_cams), float(threshold),
                 float(init_best), _np_ptr(p3d), _np_ptr(picked), _np_ptr(xyp), _np_ptr(err),

@@ -149,14 +149,22 @@ def matchSVT(S, dimGroup, *, alpha=0.1, pselect=1, tol=5e-4, maxIter=500, verbos
 
 def undistortPoints(config_path, pos_2d, omnidir=False, camparam=None):
     """multicam_toolbox.py:393-431: list of (n,2) pixel arrays per camera -> list of (n,2)
-    undistorted arrays (omnidir model; the pinhole branch reads mtx/dist from HDF5 only)."""
+    undistorted arrays.  omnidir=True: the Mei model from camparam's K / xi / D (:404-420).
+    omnidir=False: cv2.undistortPoints with the pinhole ``mtx`` / ``dist`` of every camera (:421-429;
+    the reference reads them from cam_intrinsic.h5 — here they are the entries ``camparam['mtx']``,
+    ``camparam['dist']``, as ``calib_io.read_camparam`` fills them)."""
     _need_camparam(camparam)
-    if not omnidir:
-        raise NotImplementedError("undistortPoints(omnidir=False) reads mtx/dist from cam_intrinsic.h5 "
-                                  "(multicam_toolbox.py:422-429); use cameras.Camera.undistort_points")
-    cg = group_from_camparam(camparam)
+    if omnidir:
+        cams = group_from_camparam(camparam).cameras
+    else:
+        if "mtx" not in camparam or "dist" not in camparam:
+            raise KeyError("undistortPoints(omnidir=False) needs camparam['mtx'] and camparam['dist'] "
+                           "(multicam_toolbox.py:423-425 reads them from cam_intrinsic.h5)")
+        from .cameras import Camera
+        cams = [Camera(matrix=np.asarray(m, dtype=np.float64), dist=np.asarray(d, dtype=np.float64).ravel(),
+                       name=str(i)) for i, (m, d) in enumerate(zip(camparam["mtx"], camparam["dist"]))]
     out = []
-    for cam, p in zip(cg.cameras, pos_2d):
+    for cam, p in zip(cams, pos_2d):
         p = np.asarray(p, dtype=np.float64) + 0.0
         out.append(np.squeeze(cam.undistort_points(p.reshape(1, -1, 2))))
     return out
@@ -417,3 +425,53 @@ def calc_3dtrace(p2d, camparam, thr_kp=0.3):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", category=RuntimeWarning)
         return np.nanmedian(p3d, axis=1)
+
+
+# ------------------------------------------------------------------------------------------
+# step-3 call sites of the same arithmetic (tracklets -> keypoint arrays -> batched kernels)
+# ------------------------------------------------------------------------------------------
+
+def tracklet_keypoints(trk, T, frames, n_kp):
+    """The (F, C, J, 3) keypoint array step 3 assembles frame by frame for one tracklet
+    (step3_crossframematching.py:289-297, 1116-1125): ``T[i_cam][i_frame]`` is the list of 2D tracks of a
+    camera in a frame (entry[0] = bbox id, entry[5] = (J,3) keypoints), ``trk[i_frame][i_cam]`` the bbox id
+    the tracklet uses there (-1 = none).  Cameras without a matching track are NaN."""
+    frames = np.asarray(frames, dtype=int).ravel()
+    n_cam = len(T)
+    out = np.full((frames.size, n_cam, n_kp, 3), np.nan)
+    for k, i_frame in enumerate(frames):
+        for i_cam in range(n_cam):
+            want = trk[i_frame][i_cam]
+            for tt in T[i_cam][i_frame]:
+                if tt[0] == want:
+                    out[k, i_cam] = np.asarray(tt[5], dtype=np.float64)
+    return out
+
+
+def calc_p3d(T, trk, i_frame, camparam, n_kp=MODEL_CFG["joint_num"]):
+    """get_graph's calc_p3d (step3:1115-1130): mean 3D position of a tracklet's keypoints in one frame."""
+    import warnings
+    p3d = calc_3dpose_batch(tracklet_keypoints(trk, T, [i_frame], n_kp), camparam)[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        return np.nanmean(p3d, axis=0)
+
+
+def calc_3dtrace_tracklet(trk, T, frames, camparam, config_path=None, n_kp=MODEL_CFG["joint_num"]):
+    """step3's calc_3dtrace with its own signature (:274-302): per-frame median 3D position of a tracklet
+    over ``frames`` (one launch for all of them); rows of the other frames are NaN, like the reference's."""
+    frames = np.asarray(frames, dtype=int).ravel()
+    n_frame = len(T[0])
+    trace = np.full((n_frame, 3), np.nan)
+    if frames.size:
+        trace[frames] = calc_3dtrace(tracklet_keypoints(trk, T, frames, n_kp), camparam)
+        seen = np.array([(np.asarray(trk[f]) >= 0).sum() for f in frames])
+        trace[frames[seen < 2]] = np.nan                                   # :284-285
+    return trace
+
+
+def trace_distance(p1, p2):
+    """step3's calc_dist_pose on two traces: RMS distance over the frames both have (step3:304-310)."""
+    d = np.linalg.norm(np.asarray(p1) - np.asarray(p2), axis=-1)
+    ok = ~np.isnan(d)
+    return float(np.sqrt(np.mean(d[ok] ** 2))) if ok.any() else np.nan

@@ -716,11 +716,23 @@ __global__ void __launch_bounds__(256) k_narrow(const double2* __restrict__ in, 
 }
 
 // xy / xy_picked: float64 host arrays, or (xy32 / xy_picked32) their float32 forms
+// The arrays are laid out for `ld` points; this call processes points [first, first + N) of them (the
+// *_span entry points: several devices / threads share one set of host arrays).
 static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int64_t N, int undistort, bool ransac,
                          int min_cams, double threshold, double init_best, double* p3d,
                          uint8_t* picked, double* xy_picked, float* xy_picked32, double* err, int32_t* subset,
-                         int32_t* neval) {
+                         int32_t* neval, int64_t ld = -1, int64_t first = 0) {
   if (N == 0) return M3D_OK;
+  if (ld < 0) ld = N;
+  if (xy) xy += 2 * first;
+  if (xy32) xy32 += 2 * first;
+  p3d += 3 * first;
+  if (err) err += first;
+  if (picked) picked += first;
+  if (xy_picked) xy_picked += 2 * first;
+  if (xy_picked32) xy_picked32 += 2 * first;
+  if (subset) subset += first;
+  if (neval) neval += first;
   DeviceGuard guard(rig->device);
   std::lock_guard<std::mutex> lock(rig->ws_mutex);
   const int C = rig->dev.n_cams;
@@ -745,7 +757,7 @@ static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int6
       if (C > 0) {
         if (xy32) {
           PIPE_CUDA(cudaMemcpy2DAsync(rig->ws_xy32[slot], sizeof(float) * 2 * n, xy32 + 2 * done,
-                                      sizeof(float) * 2 * N, sizeof(float) * 2 * n, C, cudaMemcpyHostToDevice, st));
+                                      sizeof(float) * 2 * ld, sizeof(float) * 2 * n, C, cudaMemcpyHostToDevice, st));
           k_widen<<<grid_for((int64_t)C * n, 256, sms), 256, 0, st>>>(
               reinterpret_cast<const float2*>(rig->ws_xy32[slot]), reinterpret_cast<double2*>(rig->ws_xy[slot]),
               (int64_t)C * n);
@@ -753,7 +765,7 @@ static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int6
           if (rc) goto pipe_failed;
         } else {
           PIPE_CUDA(cudaMemcpy2DAsync(rig->ws_xy[slot], sizeof(double) * 2 * n, xy + 2 * done,
-                                      sizeof(double) * 2 * N, sizeof(double) * 2 * n, C, cudaMemcpyHostToDevice, st));
+                                      sizeof(double) * 2 * ld, sizeof(double) * 2 * n, C, cudaMemcpyHostToDevice, st));
         }
       }
       if (!ransac) {
@@ -771,10 +783,10 @@ static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int6
         PIPE_CUDA(cudaMemcpyAsync(err + done, rig->ws_err[slot], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
       if (ransac) {
         if (picked && C > 0)
-          PIPE_CUDA(cudaMemcpy2DAsync(picked + done, (size_t)N, rig->ws_picked[slot], (size_t)n, (size_t)n, C,
+          PIPE_CUDA(cudaMemcpy2DAsync(picked + done, (size_t)ld, rig->ws_picked[slot], (size_t)n, (size_t)n, C,
                                       cudaMemcpyDeviceToHost, st));
         if (xy_picked && C > 0)
-          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked + 2 * done, sizeof(double) * 2 * N, rig->ws_xyp[slot],
+          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked + 2 * done, sizeof(double) * 2 * ld, rig->ws_xyp[slot],
                                       sizeof(double) * 2 * n, sizeof(double) * 2 * n, C, cudaMemcpyDeviceToHost, st));
         if (xy_picked32 && C > 0) {
           k_narrow<<<grid_for((int64_t)C * n, 256, sms), 256, 0, st>>>(
@@ -782,7 +794,7 @@ static int host_pipeline(m3d_rig* rig, const double* xy, const float* xy32, int6
               (int64_t)C * n);
           rc = check_launch("k_narrow");
           if (rc) goto pipe_failed;
-          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked32 + 2 * done, sizeof(float) * 2 * N, rig->ws_xyp32[slot],
+          PIPE_CUDA(cudaMemcpy2DAsync(xy_picked32 + 2 * done, sizeof(float) * 2 * ld, rig->ws_xyp32[slot],
                                       sizeof(float) * 2 * n, sizeof(float) * 2 * n, C, cudaMemcpyDeviceToHost, st));
         }
         if (subset)
@@ -846,6 +858,30 @@ int m3d_triangulate_ransac_host_f32(const m3d_rig* rig, const float* xy, int64_t
     return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_f32: NULL buffer");
   return host_pipeline(const_cast<m3d_rig*>(rig), nullptr, xy, N, undistort, true, min_cams, threshold,
                        init_best, p3d, picked, nullptr, xy_picked, err, subset, neval);
+}
+
+int m3d_triangulate_error_host_span(const m3d_rig* rig, const double* xy, int64_t N_total, int64_t first,
+                                    int64_t count, int32_t undistort, double* p3d, double* err) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_span: rig is NULL");
+  if (first < 0 || count < 0 || first + count > N_total)
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_span: span outside the arrays");
+  if (count > 0 && (!p3d || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_error_host_span: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, nullptr, count, undistort, false, 0, 0, 0, p3d, nullptr,
+                       nullptr, nullptr, err, nullptr, nullptr, N_total, first);
+}
+
+int m3d_triangulate_ransac_host_span(const m3d_rig* rig, const double* xy, int64_t N_total, int64_t first,
+                                     int64_t count, int32_t undistort, int32_t min_cams, double threshold,
+                                     double init_best, double* p3d, uint8_t* picked, double* xy_picked, double* err,
+                                     int32_t* subset, int32_t* neval) {
+  if (!rig) return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_span: rig is NULL");
+  if (first < 0 || count < 0 || first + count > N_total)
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_span: span outside the arrays");
+  if (count > 0 && (!p3d || !err || (!xy && rig->dev.n_cams > 0)))
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_ransac_host_span: NULL buffer");
+  return host_pipeline(const_cast<m3d_rig*>(rig), xy, nullptr, count, undistort, true, min_cams, threshold,
+                       init_best, p3d, picked, xy_picked, nullptr, err, subset, neval, N_total, first);
 }
 
 int m3d_host_register(void* ptr, int64_t bytes) {

@@ -695,14 +695,73 @@ __device__ __forceinline__ void dlt_solve_warp(const Gram& G, bool active, doubl
 }
 #endif  // __CUDACC__
 
-// Inhomogeneous least squares X = -pinv(A[:, :3]) A[:, 3] = -H^-1 g
-// (multicam_toolbox.py:476-484); rank-deficient H falls back to the pseudo-inverse
-// through the eigen-decomposition of H.
+// Rank-deficient normal matrix (rays that do not pin the point down: two coincident cameras, one
+// ray seen twice): np.linalg.pinv zeroes the singular values below 1e-15 sigma_max and returns the
+// MINIMUM-NORM solution.  Same result through the eigen-decomposition of H = A^T A (cyclic Jacobi):
+// X = - sum_{lambda_i > 1e-12 lambda_max} v_i (v_i . g) / lambda_i  (the squared cut-off is floored at
+// the rounding noise of forming H).
+M3D_HD_NOINLINE void ls_solve_pinv(const Gram& G, double& X, double& Y, double& Z) {
+  double A[3][3] = {{G.h[0], G.h[1], G.h[2]}, {G.h[1], G.h[3], G.h[4]}, {G.h[2], G.h[4], G.h[5]}};
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (!(off > 1e-60 * dg)) break;
+    for (int p = 0; p < 2; ++p) {
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int r = 0; r < 3; ++r) {
+          const double arp = A[r][p], arq = A[r][q];
+          A[r][p] = cs * arp - sn * arq;
+          A[r][q] = sn * arp + cs * arq;
+        }
+        for (int r = 0; r < 3; ++r) {
+          const double apr = A[p][r], aqr = A[q][r];
+          A[p][r] = cs * apr - sn * aqr;
+          A[q][r] = sn * apr + cs * aqr;
+        }
+        for (int r = 0; r < 3; ++r) {
+          const double vrp = V[r][p], vrq = V[r][q];
+          V[r][p] = cs * vrp - sn * vrq;
+          V[r][q] = sn * vrp + cs * vrq;
+        }
+      }
+    }
+  }
+  double lmax = A[0][0];
+  if (A[1][1] > lmax) lmax = A[1][1];
+  if (A[2][2] > lmax) lmax = A[2][2];
+  X = Y = Z = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    if (A[i][i] > 1e-12 * lmax) {
+      const double c = -(V[0][i] * G.g[0] + V[1][i] * G.g[1] + V[2][i] * G.g[2]) / A[i][i];
+      X += c * V[0][i];
+      Y += c * V[1][i];
+      Z += c * V[2][i];
+    }
+  }
+  if (!(lmax > 0.0)) X = Y = Z = qnan();
+}
+
+// Inhomogeneous least squares X = -pinv(A[:, :3]) A[:, 3] (multicam_toolbox.py:476-484): -H^-1 g
+// through the adjugate for a well-conditioned H, the pseudo-inverse (ls_solve_pinv) when H is
+// numerically rank-deficient.
 M3D_HD void ls_solve(const Gram& G, double& X, double& Y, double& Z) {
   const double a = G.h[0], b = G.h[1], c = G.h[2], d = G.h[3], e = G.h[4], f = G.h[5];
   const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
   const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
   const double det = a * c00 + b * c01 + c * c02;
+  const double tr = a + d + f;
+  // det = l1 l2 l3 <= (tr/3)^3: a ratio below 1e-11 means lambda_min / lambda_max < ~1e-10
+  if (!(det > 1e-11 * tr * tr * tr)) {
+    const Gram tmp = G;
+    ls_solve_pinv(tmp, X, Y, Z);
+    return;
+  }
   const double idet = 1.0 / det;
   X = -(c00 * G.g[0] + c01 * G.g[1] + c02 * G.g[2]) * idet;
   Y = -(c01 * G.g[0] + c11 * G.g[1] + c12 * G.g[2]) * idet;

@@ -306,6 +306,8 @@ int m3d_triangulate_possible(const m3d_rig* rig, const double* xy, int64_t N, in
   const int C = rig->dev.n_cams;
   if (P < 1 || C * P > POSS_SLOTS)
     return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: cameras * candidates must be between 1 and 32");
+  if (P > 15)  // the chosen candidate of a camera is kept in 4 bits, 15 = "none" (m3d_possible.cuh)
+    return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: at most 15 candidates per camera");
   if (N == 0) return M3D_OK;
   if (!p3d || !err || (!xy && C > 0)) return fail(M3D_ERR_INVALID, "m3d_triangulate_possible: NULL buffer");
   const size_t smem = possible_smem_bytes();

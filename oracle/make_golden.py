@@ -280,6 +280,39 @@ def case_svt(ref, name, n_frames, seed, drop=0.15, p_cid=0.7, p_cid_wrong=0.1, n
                         match=np.array(matches), n_frames=np.array(n_frames))
 
 
+def case_ls_degenerate(ref, name, seed):
+    """mct.triangulatePoints (multicam_toolbox.py:433-486) where the rays do NOT determine the point: two
+    coincident cameras see it (rank-2 system -> np.linalg.pinv returns the minimum-norm solution), next to
+    ordinary well-posed points."""
+    from src.utils import multicam_toolbox as mct
+    import cv2
+    cams = synth.make_rig(4, "pinhole", seed=seed)
+    cams[1] = dict(cams[0], name="2")                                   # camera 2 coincides with camera 1
+    camparam = {"camera_id": [d["name"] for d in cams], "K": [], "xi": [], "D": [], "rvecs": [], "tvecs": [], "pmat": []}
+    for d in cams:
+        R, _ = cv2.Rodrigues(np.array(d["rotation"]))
+        t = np.array(d["translation"]).reshape(3, 1)
+        camparam["K"].append(np.array(d["matrix"]))
+        camparam["xi"].append(np.zeros((1, 1)))
+        camparam["D"].append(np.zeros((1, 4)))
+        camparam["rvecs"].append(np.array(d["rotation"]).reshape(3, 1))
+        camparam["tvecs"].append(t)
+        camparam["pmat"].append(np.hstack([R, t]))
+    rng = np.random.default_rng(seed)
+    n = 12
+    X = rng.uniform([-500, -500, 0], [500, 500, 900], size=(n, 3))
+    und = []
+    for P in camparam["pmat"]:
+        Xc = X @ P[:, :3].T + P[:, 3]
+        und.append(Xc[:, :2] / Xc[:, 2:3])
+    use = np.ones((n, 4), dtype=bool)
+    use[:6, 2:] = False                                                 # points 0..5: only the coincident pair
+    p3d = mct.triangulatePoints("", und, use, True, camparam=camparam)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rig_arrays(cams), ls_xy=np.array(und), ls_use=use,
+                        ls_p3d=p3d, X_true=X)
+    print(name, "degenerate rows", p3d[:2], "regular", np.abs(p3d[6:] - X[6:]).max())
+
+
 def case_possible(ref, name, n_cams, n_frames, seed, n_possible=2, min_cams=2, p_swap=0.3, p_missing=0.2):
     """CameraGroup.triangulate_possible with P candidates per camera (cameras.py:639-724): the
     second candidate is a distractor (N(0, 40 px) away) or missing; in 30 % of the (camera, point)
@@ -443,6 +476,7 @@ def main():
         "viterbi_p1": lambda: case_viterbi("viterbi_p1", 400, 6, 1, S + 31),
         "viterbi_p2": lambda: case_viterbi("viterbi_p2", 150, 4, 2, S + 32),
         "viterbi_p1_nb4": lambda: case_viterbi("viterbi_p1_nb4", 120, 3, 1, S + 33, n_back=4, offset_threshold=10),
+        "ls_degenerate": lambda: case_ls_degenerate(ref, "ls_degenerate", S + 71),
         "svt_ragged_f240": lambda: case_svt(ref, "svt_ragged_f240", 240, S + 61),
         "optim_c8_n2": lambda: case_optim(ref, "optim_c8_n2", 8, 48, S + 51),
         "optim_c4_n1_huber": lambda: case_optim(ref, "optim_c4_n1_huber", 4, 30, S + 52, n_deriv=1, reproj_loss="huber",

@@ -75,6 +75,19 @@ def test_gpu_crossview_golden(name):
         assert abs(int(its[f]) - it_ref) <= 2
 
 
+def test_gpu_ls_rank_deficient_matches_pinv():
+    """mct.triangulatePoints with two coincident cameras: np.linalg.pinv's minimum-norm solution (golden from
+    the executed reference), next to well-posed points."""
+    g, cams = fixtures.load_golden("ls_degenerate")
+    cp = camparam_from_golden(g)
+    p3 = cv.triangulatePoints("", list(g["ls_xy"]), g["ls_use"], True, camparam=cp)
+    ref = g["ls_p3d"]
+    assert np.isfinite(p3).all()
+    assert np.abs(p3[6:] - ref[6:]).max() <= 1e-6
+    # the minimum-norm solutions: compare relative to their size (the cut-off acts on a 1e-16-level quantity)
+    assert np.abs(p3[:6] - ref[:6]).max() <= 1e-6 * np.abs(ref[:6]).max()
+
+
 def test_gpu_match_svt_240_reference_frames():
     """matchSVT bit-exact on 240 keyframes executed by the reference (ragged detection counts, identity
     term on, every 4th frame with heavy 2D noise: frames that do not settle into clean blocks)."""

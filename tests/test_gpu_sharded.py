@@ -71,3 +71,52 @@ def test_nccl_sharded_equals_single_gpu(tmp_path, n_frames, tile, ransac):
     r = np.load(tmp)
     assert r["n"] == n_frames * 34
     assert bool(r["ok3"]) and bool(r["oke"]), "sharded result differs from the single-GPU result"
+
+
+def _span_case():
+    from macaque_3d_pose_estimation_b200 import synth
+    from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+    from oracle import cameragroup as og
+    from oracle import fixtures
+    import __graft_entry__ as ge
+    ge.build_library()
+    dicts = synth.make_rig(8, "pinhole", seed=20261020)
+    cams = fixtures.cams_from_dicts(dicts)
+    X = synth.make_tracks(700, 2, seed=9).reshape(-1, 3)
+    p2 = synth.corrupt(og.project(cams, X), seed=9, p_outlier=0.2, p_missing=0.1)
+    return CameraGroup.from_dicts(dicts), p2
+
+
+def test_host_span_entry_points_cover_the_arrays():
+    """m3d_triangulate_*_host_span: disjoint spans of one set of host arrays, processed by separate calls
+    (two threads on one GPU here), give exactly the single-call result."""
+    cg, p2 = _span_case()
+    cg.device = 0
+    ref3, refe = cg.triangulate_with_error(p2)
+    rr = cg.triangulate_ransac(p2, min_cams=2, return_stats=True)
+    cg2, _ = _span_case()
+    cg2._host_devices = lambda n: [0, 0, 0]                    # three spans, one device
+    got3, gote = cg2.triangulate_with_error(p2)
+    assert np.array_equal(got3, ref3, equal_nan=True) and np.array_equal(gote, refe, equal_nan=True)
+    gr = cg2.triangulate_ransac(p2, min_cams=2, return_stats=True)
+    for a, b in zip(rr, gr):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_single_process_spreads_numpy_input_over_all_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 visible GPUs (this box has %d)" % torch.cuda.device_count())
+    cg, p2 = _span_case()
+    cg.device = 0
+    ref3, refe = cg.triangulate_with_error(p2)
+    cg2, _ = _span_case()
+    cg2.MULTI_GPU_MIN_POINTS = 1000
+    assert cg2._host_devices(p2.shape[1]) == list(range(torch.cuda.device_count()))
+    got3, gote = cg2.triangulate_with_error(p2)
+    assert np.array_equal(got3, ref3, equal_nan=True) and np.array_equal(gote, refe, equal_nan=True)
+    rr = cg.triangulate_ransac(p2, return_stats=True)
+    gr = cg2.triangulate_ransac(p2, return_stats=True)
+    for a, b in zip(rr, gr):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert len(cg2._rig_cache[1]) == torch.cuda.device_count()   # one rig per GPU
