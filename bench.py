@@ -854,7 +854,7 @@ def main():
     ap.add_argument("--workload", choices=["dlt", "ransac"], default="ransac")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 1e6)")
-    ap.add_argument("--rounds", type=int, default=16, help="tile rounds per step of the sharded RANSAC")
+    ap.add_argument("--rounds", type=int, default=8, help="tile rounds per step of the sharded RANSAC")
     ap.add_argument("--e2e-points", type=int, default=20000000,
                     help="joint-instances per GPU of the e2e run (the same at every N)")
     ap.add_argument("--cameras", type=int, default=8, help="cameras of the synthetic ring rig (BASELINE: 8; config 5: 16)")

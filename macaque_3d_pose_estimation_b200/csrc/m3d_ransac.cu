@@ -62,8 +62,8 @@ static int ensure_pool(const m3d_rig* rig) {
 }
 
 // joint-instances per internal launch of the pruned search: bounds the queue of undecided points
-// (304 bytes per record at C = 8) + slots to 3 GB
-static const int64_t kCertChunk = 1 << 23;
+// (304 bytes per record at C = 8) + slots to 6 GB
+static const int64_t kCertChunk = 1 << 24;
 
 // Pruned subset search (m3d_ransac_cert.cuh): setup -> persistent search -> emit, per chunk.
 static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, int undistort, int min_cams,
@@ -88,6 +88,10 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
   M3D_CUDA(scratch.alloc((void**)&over, sizeof(unsigned int) * (size_t)chunk, rig->pool));
   const bool po = (rig->dev.flags & RIG_HAS_NONPINHOLE) == 0;
   // developer switch: CTAs per SM of the persistent search kernel (2 = 255 registers, 3 = 168)
+  // developer switch: M3D_CERT_V1=1 runs the round-2a split (full-set solve in the thread-per-point kernel)
+  static const bool cert_v1 = [] { const char* e = getenv("M3D_CERT_V1"); return e && atoi(e) != 0; }();
+  // developer switch: M3D_CERT_EMIT=1 keeps the result slots + k_ransac_emit pass in the v2 split
+  static const bool cert_emit = [] { const char* e = getenv("M3D_CERT_EMIT"); return e && atoi(e) != 0; }();
   static const int setup_ctas = [] { const char* e = getenv("M3D_CERT_SETUP_CTAS"); return e ? atoi(e) : 0; }();
   static const int search_ctas = [] { const char* e = getenv("M3D_CERT_CTAS"); return e ? atoi(e) : 0; }();
   // evaluations a lane of k_cert_search spends on one point before it parks the search for
@@ -100,40 +104,60 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
   for (int64_t n0 = 0; n0 < N; n0 += chunk) {
     const int64_t n = (N - n0) < chunk ? (N - n0) : chunk;
     M3D_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), st));
+    // v2 split: the search kernels write the reference's outputs themselves (no slots, no emit pass)
+    CertOutputs outs = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, N, n0};
+    if (!cert_v1 && !cert_emit) outs = CertOutputs{p3d, picked, xy_picked, err, subset, neval, N, n0};
     int64_t blocksA = (n + 127) / 128;
     const int64_t cap = (int64_t)sms * 3 * 32;
     if (blocksA > cap) blocksA = cap;
-#define CALLA(PO, NC, MB)                                                                                    \
-  M3dKernelTimer timer__("k_cert_setup", st);                                                                \
-  k_cert_setup<PO, NC, MB><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,   \
-                                                              min_cams, threshold, init_best, slots, rec, counters)
-    if (C == 8) {
-      if (setup_ctas == 4) { if (po) { CALLA(true, 8, 4); } else { CALLA(false, 8, 4); } }
-      else if (setup_ctas == 2) { if (po) { CALLA(true, 8, 2); } else { CALLA(false, 8, 2); } }
-      else { if (po) { CALLA(true, 8, 3); } else { CALLA(false, 8, 3); } }
+    if (!cert_v1) {
+#define CALLP(PO, NC, MB)                                                                                    \
+  M3dKernelTimer timer__("k_cert_prep", st);                                                                 \
+  k_cert_prep<PO, NC, MB><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,    \
+                                                             threshold, init_best, rec, counters)
+      if (C == 8) {
+        if (setup_ctas == 3) { if (po) { CALLP(true, 8, 3); } else { CALLP(false, 8, 3); } }
+        else { if (po) { CALLP(true, 8, 4); } else { CALLP(false, 8, 4); } }
+      } else {
+        if (po) { CALLP(true, 0, 2); } else { CALLP(false, 0, 2); }
+      }
+#undef CALLP
     } else {
-      if (po) { CALLA(true, 0, 2); } else { CALLA(false, 0, 2); }
-    }
-#undef CALLA
+#define CALLA(PO, NC, MB)                                                                                    \
+    M3dKernelTimer timer__("k_cert_setup", st);                                                                \
+    k_cert_setup<PO, NC, MB><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,   \
+                                                                min_cams, threshold, init_best, slots, rec, counters)
+      if (C == 8) {
+        if (setup_ctas == 4) { if (po) { CALLA(true, 8, 4); } else { CALLA(false, 8, 4); } }
+        else if (setup_ctas == 2) { if (po) { CALLA(true, 8, 2); } else { CALLA(false, 8, 2); } }
+        else { if (po) { CALLA(true, 8, 3); } else { CALLA(false, 8, 3); } }
+      } else {
+        if (po) { CALLA(true, 0, 2); } else { CALLA(false, 0, 2); }
+      }
+  #undef CALLA
+  }
     rc = check_launch("k_cert_setup");
     if (rc) return rc;
 #define CALLB(PO, NC, MB)                                                                                    \
   do {                                                                                                       \
     auto kfn = k_cert_search<PO, NC, MB>;                                                                    \
     M3dKernelTimer timer__("k_cert_search", st);                                                             \
+    const size_t smem_s = (size_t)2 * C * 128 * 16;                                                          \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);                     \
     int per_sm = 0;                                                                                          \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, 0);                                     \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem_s);                                \
     if (per_sm < 1) per_sm = 1;                                                                              \
     int64_t blocks = (int64_t)sms * per_sm;                                                                  \
     const int64_t need = (n + 127) / 128;                                                                    \
     if (blocks > need) blocks = need;                                                                        \
-    kfn<<<(unsigned)blocks, 128, 0, st>>>(rig->dev, rig->cumb_g, min_cams, threshold, init_best, slots, rec, \
-                                          counters, counters + 1, over, counters + 2, lane_limit);           \
+    kfn<<<(unsigned)blocks, 128, smem_s, st>>>(rig->dev, rig->cumb_g, min_cams, threshold, init_best, slots, rec, \
+                                          counters, counters + 1, over, counters + 2, lane_limit, outs);     \
   } while (0)
     if (C == 8) {
       if (search_ctas == 2) { if (po) CALLB(true, 8, 2); else CALLB(false, 8, 2); }
-      else if (search_ctas == 4) { if (po) CALLB(true, 8, 4); else CALLB(false, 8, 4); }
-      else { if (po) CALLB(true, 8, 3); else CALLB(false, 8, 3); }
+      else if (search_ctas == 5) { if (po) CALLB(true, 8, 5); else CALLB(false, 8, 5); }
+      else if (search_ctas == 3) { if (po) CALLB(true, 8, 3); else CALLB(false, 8, 3); }
+      else { if (po) CALLB(true, 8, 4); else CALLB(false, 8, 4); }
     } else {
       if (po) CALLB(true, 0, 2); else CALLB(false, 0, 2);
     }
@@ -145,7 +169,7 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
       const unsigned ob = (unsigned)(sms * 2);
 #define CALLO(PO, NC)                                                                                        \
   k_cert_overflow<PO, NC><<<ob, 128, 0, st>>>(rig->dev, rig->cumb_g, min_cams, threshold, init_best, slots, rec, \
-                                              over, counters + 2, counters + 3)
+                                              over, counters + 2, counters + 3, outs)
       if (C == 8) {
         if (po) CALLO(true, 8); else CALLO(false, 8);
       } else {
@@ -155,13 +179,15 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
     }
     rc = check_launch("k_cert_overflow");
     if (rc) return rc;
-    {
-      M3dKernelTimer timer__("k_ransac_emit", st);
-      k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
-                                                           subset, neval);
+    if (!outs.p3d) {
+      {
+        M3dKernelTimer timer__("k_ransac_emit", st);
+        k_ransac_emit<<<grid_for(n, 256, sms), 256, 0, st>>>(C, xy, N, n0, n, slots, p3d, picked, xy_picked, err,
+                                                             subset, neval);
+      }
+      rc = check_launch("k_ransac_emit");
+      if (rc) return rc;
     }
-    rc = check_launch("k_ransac_emit");
-    if (rc) return rc;
   }
   return M3D_OK;
 }

@@ -95,8 +95,10 @@ M3D_HD void cert_undistort(const RigDev& rig, const XY* raw, int undistort, XY* 
 
 // triangulate from the usable cameras of `kept`, score against the raw pixels of all of `kept`
 // (cameras.py:697-701): mean reprojection error, NaN when undefined
-template <bool PO, int NC>
-M3D_HD double cert_eval(const RigDev& rig, const XY* raw, const XY* xh, uint32_t kept, uint32_t uc, double& X,
+// (RV / XV: anything indexable by camera that yields an XY — plain arrays, or the shared-memory views
+// of k_cert_search)
+template <bool PO, int NC, class RV, class XV>
+M3D_HD double cert_eval(const RigDev& rig, const RV& raw, const XV& xh, uint32_t kept, uint32_t uc, double& X,
                         double& Y, double& Z) {
   constexpr int CC = NC > 0 ? NC : M3D_MAXC;
   const int C = NC > 0 ? NC : rig.n_cams;
@@ -106,8 +108,12 @@ M3D_HD double cert_eval(const RigDev& rig, const XY* raw, const XY* xh, uint32_t
   Gram G;
   gram_zero(G);
 #pragma unroll
-  for (int c = 0; c < CC; ++c)
-    if (c < C && ((uc >> (TOP - c)) & 1u)) gram_add_camera(G, rig.cam[c], xh[c].x, xh[c].y);
+  for (int c = 0; c < CC; ++c) {
+    if (c < C && ((uc >> (TOP - c)) & 1u)) {
+      const XY q = xh[c];
+      gram_add_camera(G, rig.cam[c], q.x, q.y);
+    }
+  }
   dlt_solve(G, X, Y, Z);
   double sum = 0.0;
   int m = 0;
@@ -116,7 +122,8 @@ M3D_HD double cert_eval(const RigDev& rig, const XY* raw, const XY* xh, uint32_t
     if (c < C && ((kept >> (TOP - c)) & 1u)) {
       double pu, pv;
       project_point<false, PO>(rig.cam[c], X, Y, Z, pu, pv);
-      const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
+      const XY q = raw[c];
+      const double e = residual_norm(q.x - pu, q.y - pv);
       if (e == e) {
         sum += e;
         ++m;
@@ -127,49 +134,62 @@ M3D_HD double cert_eval(const RigDev& rig, const XY* raw, const XY* xh, uint32_t
 }
 
 // pair certificates at residual budget rho (m3d_cert.h): badrow[p] = certified-bad partners of bit
-// position p at HIGHER positions
+// position p at HIGHER positions.  rho_full > 0: also report (full_bad) whether some pair is flagged
+// at that larger budget — the budget of the FULL set, |S| = k — so that the full-set solve itself
+// can be skipped.  Straight-line per pair (no branch): a camera that cannot take part (no
+// certificate, unusable view, non-finite centre) carries an infinite half-budget, which makes the
+// right-hand side infinite; a NaN form compares false.
 template <int NC>
 M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, const XY* xh, uint32_t u,
-                       double rho, uint32_t* badrow) {
+                       double rho, uint32_t* badrow, double rho_full = 0.0, bool* full_bad = nullptr) {
   constexpr int CC = NC > 0 ? NC : M3D_MAXC;
   const int C = NC > 0 ? NC : rig.n_cams;
   const uint32_t TOP = (uint32_t)(C - 1);
-  double dl[CC];
-  uint32_t pairable = 0;
+  // half budgets per camera: D = h[a] + h[b] = (rho + delta_a + delta_b) (1 + 1e-9); the slack on D
+  // covers the comparison (the right-hand side grows faster than linearly in D)
+  double h[CC], hf[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
-    dl[c] = 0.0;
+    h[c] = hf[c] = pos_inf();
     badrow[c] = 0;
     if (c < C && ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0) {
       double pu, pv;
       distort_pinhole<false>(rig.cam[c], xh[c].x, xh[c].y, pu, pv);
       const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
       if (e < 1e3) {  // finite centre, finite raw pixel
-        dl[c] = e;
-        pairable |= 1u << (TOP - c);
+        h[c] = (e + 0.5 * rho) * (1.0 + 1e-9);
+        hf[c] = (e + 0.5 * rho_full) * (1.0 + 1e-9);
       }
     }
   }
+  bool fb = false;
 #pragma unroll
   for (int a = 0; a < CC; ++a) {
 #pragma unroll
     for (int b = a + 1; b < CC; ++b) {
-      if (b >= C || ((pairable >> (TOP - a)) & (pairable >> (TOP - b)) & 1u) == 0) continue;
+      if (b >= C) continue;
       const double* E = cert.E[pair_index(a, b, C)];
       const double ax = xh[a].x, ay = xh[a].y, qx = xh[b].x, qy = xh[b].y;
-      const double ea0 = E[0] * ax + E[1] * ay + E[2];
-      const double ea1 = E[3] * ax + E[4] * ay + E[5];
-      const double ea2 = E[6] * ax + E[7] * ay + E[8];
-      const double F = qx * ea0 + qy * ea1 + ea2;
-      const double tb0 = E[0] * qx + E[3] * qy + E[6];
-      const double tb1 = E[1] * qx + E[4] * qy + E[7];
+      const double ea0 = fma(E[0], ax, fma(E[1], ay, E[2]));
+      const double ea1 = fma(E[3], ax, fma(E[4], ay, E[5]));
+      const double ea2 = fma(E[6], ax, fma(E[7], ay, E[8]));
+      const double F = fabs(fma(qx, ea0, fma(qy, ea1, ea2)));
+      const double tb0 = fma(E[0], qx, fma(E[3], qy, E[6]));
+      const double tb1 = fma(E[1], qx, fma(E[4], qy, E[7]));
       const double A = (fabs(tb0) + fabs(tb1)) * cert.inv_mf[a];
       const double B = (fabs(ea0) + fabs(ea1)) * cert.inv_mf[b];
-      const double D = rho + dl[a] + dl[b];
-      const double rhs = ((A > B ? A : B) + 0.25 * E[9] * D) * D;
-      if (fabs(F) > rhs * (1.0 + 1e-9)) badrow[TOP - b] |= 1u << (TOP - a);
+      const double M = A > B ? A : B;
+      const double g = 0.25 * E[9];
+      const double D = h[a] + h[b];
+      const bool bad = F > fma(g, D, M) * D;
+      badrow[TOP - b] |= bad ? (1u << (TOP - a)) : 0u;
+      if (full_bad) {
+        const double Df = hf[a] + hf[b];
+        fb = fb || (F > fma(g, Df, M) * Df);
+      }
     }
   }
+  if (full_bad) *full_bad = fb;
 }
 
 // residual budget of the pair certificates: the weakest radius any subset after the full set can
@@ -420,12 +440,117 @@ k_cert_setup(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev
   }
 }
 
+// v2 split: NO solve here.  Undistort, pair flags (at the budget of the subsets after the full set, and
+// whether the full set itself is already excluded at ITS budget), one record per point for EVERY point.
+// All solves — the full set's included — then run in k_cert_search with all 32 lanes busy; for the
+// ~75 % of the points whose full set holds a flagged pair the full-set solve disappears altogether.
+template <bool PO, int NC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_cert_prep(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev cert,
+            const double* __restrict__ xy, int64_t ld, int64_t n0, int64_t n, int undistort, double thr,
+            double init_best, double2* __restrict__ rec, unsigned int* __restrict__ n_rec) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const int C = NC > 0 ? NC : rig.n_cams;
+  const int F = cert_record_fields(C);
+  const double T1 = thr < init_best ? thr : init_best;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    XY raw[CC], xh[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      if (c < C) {
+        const double2 q = ld_xy(xy, (int64_t)c * ld + n0 + i);
+        raw[c].x = q.x;
+        raw[c].y = q.y;
+      }
+    }
+    uint32_t v, u;
+    cert_undistort<PO, NC>(rig, raw, undistort, xh, v, u);
+    const int k = __popc(v);
+    uint32_t badrow[CC];
+    bool full_bad = false;
+    cert_pairs<NC>(rig, cert, raw, xh, u, cert_rho(T1, k), badrow, cert_rho(T1, k + 1), &full_bad);
+    // record i of this launch (the queue is the identity: every point has one)
+    const unsigned int q = (unsigned int)i;
+    double2* r = rec + ((size_t)(q >> 5) * F) * 32 + (q & 31u);
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      if (c < C) {
+        r[(size_t)c * 32] = make_double2(raw[c].x, raw[c].y);
+        r[(size_t)(C + c) * 32] = make_double2(xh[c].x, xh[c].y);
+      }
+    }
+    // m0.z: bit 0 = the full set is still to be visited, bit 1 = it holds no flagged pair (solve it),
+    // bit 2 = record of the v2 split (the full set's error has not been recorded anywhere)
+    reinterpret_cast<uint4*>(r)[(size_t)(2 * C) * 32] =
+        make_uint4(v | (u << 16), (uint32_t)i, 1u | (full_bad ? 0u : 2u) | 4u, 0u);
+    r[(size_t)(2 * C + 1) * 32] = make_double2(init_best, qnan());
+    r[(size_t)(2 * C + 2) * 32] = make_double2(qnan(), qnan());
+#pragma unroll
+    for (int g = 0; g < (CC + 7) / 8; ++g) {
+      if (8 * g < C) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p0 = 8 * g + 2 * j, p1 = p0 + 1;
+          w[j] = (p0 < CC ? (badrow[p0 < CC ? p0 : 0] & 0xffffu) : 0u) |
+                 ((p1 < CC ? (badrow[p1 < CC ? p1 : 0] & 0xffffu) : 0u) << 16);
+        }
+        reinterpret_cast<uint4*>(r)[(size_t)(2 * C + 3 + g) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    if (i == 0) *n_rec = (unsigned int)n;
+  }
+}
+
+// The reference's outputs of one launch (cameras.py:715-724); NULL members are not written.  When `p3d`
+// is NULL the kernels fill the result slot instead and k_ransac_emit expands it.
+struct CertOutputs {
+  double* p3d;
+  uint8_t* picked;
+  double* xy_picked;
+  double* err;
+  int32_t* subset;
+  int32_t* neval;
+  int64_t ld;  // points per camera plane of picked / xy_picked
+  int64_t n0;  // first point of this launch
+};
+
+// Result of one point straight into the output arrays (v2 split: queue order is point order, so the
+// stores of neighbouring lanes and warps meet in L2 before they reach DRAM).
+template <int NC, class RV>
+__device__ __forceinline__ void cert_write_point(const CertOutputs& o, int C, uint32_t idx, uint32_t v, uint32_t best_d,
+                                                 bool have, double best_err, double bx, double by, double bz,
+                                                 int32_t s_sel, int32_t ne, const RV& raw) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  const int64_t i = o.n0 + (int64_t)idx;
+  o.p3d[3 * i] = bx;
+  o.p3d[3 * i + 1] = by;
+  o.p3d[3 * i + 2] = bz;
+  o.err[i] = have ? best_err : 0.0;  // errors default to 0.0 (cameras.py:675)
+  if (o.subset) o.subset[i] = have ? s_sel : -1;
+  if (o.neval) o.neval[i] = ne;
+  const uint32_t sel = have ? (v & ~best_d) : 0u;
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    if (c < C) {
+      const bool in = (sel >> (C - 1 - c)) & 1u;
+      if (o.picked) o.picked[(int64_t)c * o.ld + i] = in ? 1 : 0;
+      if (o.xy_picked) {
+        XY q = raw[c];
+        st_xy(o.xy_picked, (int64_t)c * o.ld + i, in ? q.x : qnan(), in ? q.y : qnan());
+      }
+    }
+  }
+}
+
 template <bool PO, int NC, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ cumb, int min_cams, double thr,
               double init_best, RansacSlot* __restrict__ slots, double2* __restrict__ rec,
               const unsigned int* __restrict__ n_rec, unsigned int* __restrict__ counter,
-              unsigned int* __restrict__ over, unsigned int* __restrict__ n_over, int lane_limit) {
+              unsigned int* __restrict__ over, unsigned int* __restrict__ n_over, int lane_limit,
+              const CertOutputs outs) {
   constexpr int CC = NC > 0 ? NC : M3D_MAXC;
   constexpr unsigned FULLM = 0xffffffffu;
   const int C = NC > 0 ? NC : rig.n_cams;
@@ -433,11 +558,20 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
   const double T1 = thr < init_best ? thr : init_best;
   const int lane = threadIdx.x & 31;
   const unsigned int total = *n_rec;
-  XY raw[CC], xh[CC];
+  // the observations of a lane's point live in shared memory ([field][thread], 16-byte accesses by
+  // consecutive lanes: conflict-free): 64 registers less per thread, a quarter more resident warps
+  extern __shared__ __align__(16) unsigned char smem_search[];
+  struct View {
+    XY* base;
+    __device__ __forceinline__ XY operator[](int c) const { return base[c * 128]; }
+  };
+  XY* sbase = reinterpret_cast<XY*>(smem_search) + threadIdx.x;
+  const View raw{sbase}, xh{sbase + (size_t)C * 128};
   uint32_t badrow[CC];
   uint32_t v = 0, u = 0, d = 0, best_d = 0, idx = 0, qrec = 0;
   int pass = 1, n_done = 0;
   bool active = false, drained = false, have = false;
+  bool first = false, full_ok = false, is_v2 = false;  // v2 records: the full set is the first candidate (if not excluded)
   double best_err = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
 #pragma unroll 1
   for (;;) {
@@ -456,8 +590,8 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
           for (int c = 0; c < CC; ++c) {
             if (c < C) {
               const double2 a = r[(size_t)c * 32], b = r[(size_t)(C + c) * 32];
-              raw[c].x = a.x, raw[c].y = a.y;
-              xh[c].x = b.x, xh[c].y = b.y;
+              reinterpret_cast<double2*>(raw.base)[c * 128] = a;
+              reinterpret_cast<double2*>(xh.base)[c * 128] = b;
             }
           }
           const uint4 m0 = reinterpret_cast<const uint4*>(r)[(size_t)(2 * C) * 32];
@@ -485,6 +619,9 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
           qrec = q;
           n_done = 0;
           d = 0;
+          first = (m0.z & 1u) != 0;
+          full_ok = (m0.z & 2u) != 0;
+          is_v2 = (m0.z & 4u) != 0;
         } else {
           drained = true;
         }
@@ -494,23 +631,32 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
     if (active) {
       // ---- every lane moves to its next surviving subset (one convergent pass per trip)
       bool stop = false, ran_out = false;
-      d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
-      if (d == 0 && pass == 1 && T1 < best_err) {
-        // nothing under T1: rescan everything for the strict arg-min, without pruning
+      bool at_full = false;  // the candidate of this trip is the full set (d == 0, always admissible: :691)
+      if (first && full_ok) {
+        at_full = true;
+      } else {
+        d = cert_advance<NC>(v, cert_next(v, d), badrow, min_cams);
+      }
+      first = false;
+      if (!at_full && d == 0 && pass == 1 && T1 < best_err) {
+        // nothing under T1: rescan everything for the strict arg-min, without pruning.  v2 records
+        // restart AT the full set (its error was never recorded), v1 records after it.
         pass = 2;
 #pragma unroll
         for (int p = 0; p < CC; ++p) badrow[p] = 0;
-        d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
+        if (is_v2) at_full = true;
+        else d = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
       }
-      if (d == 0) {
+      if (at_full) d = 0;
+      if (!at_full && d == 0) {
         stop = ran_out = true;
-      } else if (n_done >= lane_limit) {
+      } else if (!at_full && n_done >= lane_limit) {
         // a long search (a point without a clean subset, a point far outside the images) would
         // keep this lane — in the end this whole warp — busy for hundreds of trips: park its
         // state in the record and hand it to the warp-cooperative kernel
         double2* r = rec + ((size_t)(qrec >> 5) * F) * 32 + (qrec & 31u);
         reinterpret_cast<uint4*>(r)[(size_t)(2 * C) * 32] =
-            make_uint4(v | (u << 16), idx, d, (uint32_t)pass | (have ? 256u : 0u) | (best_d << 16));
+            make_uint4(v | (u << 16), idx, d, (uint32_t)pass | (have ? 256u : 0u) | (is_v2 ? 512u : 0u) | (best_d << 16));
         r[(size_t)(2 * C + 1) * 32] = make_double2(best_err, bx);
         r[(size_t)(2 * C + 2) * 32] = make_double2(by, bz);
         over[atomicAdd(n_over, 1u)] = qrec;
@@ -535,13 +681,18 @@ k_cert_search(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ c
         int ne = 1;
         if (ran_out) ne += count_adm(cumb, (1u << k) - 1u, k - min_cams);
         else ne += count_adm(cumb, s_sel, k - min_cams);
-        RansacSlot* sl = slots + idx;
-        sl->best_err = best_err;
-        sl->bx = bx;
-        sl->by = by;
-        sl->bz = bz;
-        sl->best_s = have ? (int32_t)s_sel : -1;
-        sl->neval = ne;
+        if (outs.p3d) {
+          cert_write_point<NC>(outs, C, idx, v, best_d, have, best_err, bx, by, bz, (int32_t)s_sel, ne, raw);
+        } else {
+          RansacSlot* sl = slots + idx;
+          sl->best_err = best_err;
+          sl->bx = bx;
+          sl->by = by;
+          sl->bz = bz;
+          sl->masks = __brev(v) >> (32 - C);  // physical camera numbering for k_ransac_emit
+          sl->best_s = have ? (int32_t)s_sel : -1;
+          sl->neval = ne;
+        }
         active = false;
       }
     }
@@ -557,7 +708,7 @@ __global__ void __launch_bounds__(128, 2)
 k_cert_overflow(const __grid_constant__ RigDev rig, const uint32_t* __restrict__ cumb, int min_cams, double thr,
                 double init_best, RansacSlot* __restrict__ slots, const double2* __restrict__ rec,
                 const unsigned int* __restrict__ over, const unsigned int* __restrict__ n_over,
-                unsigned int* __restrict__ counter) {
+                unsigned int* __restrict__ counter, const CertOutputs outs) {
   constexpr int CC = NC > 0 ? NC : M3D_MAXC;
   constexpr unsigned FULLM = 0xffffffffu;
   const int C = NC > 0 ? NC : rig.n_cams;
@@ -588,6 +739,7 @@ k_cert_overflow(const __grid_constant__ RigDev rig, const uint32_t* __restrict__
     uint32_t dcur = m0.z;
     int pass = (int)(m0.w & 255u);
     bool have = (m0.w & 256u) != 0;
+    const bool is_v2 = (m0.w & 512u) != 0;
     uint32_t best_d = m0.w >> 16;
     const double2 b0 = r[(size_t)(2 * C + 1) * 32], b1 = r[(size_t)(2 * C + 2) * 32];
     double best_err = b0.x, bx = b0.y, by = b1.x, bz = b1.y;
@@ -614,6 +766,12 @@ k_cert_overflow(const __grid_constant__ RigDev rig, const uint32_t* __restrict__
           pass = 2;
 #pragma unroll
           for (int p = 0; p < CC; ++p) badrow[p] = 0;
+          if (is_v2) {
+            // v2 records never recorded the full set's error: it is the first candidate of the arg-min scan
+            double X0, Y0, Z0;
+            const double e0 = cert_eval<PO, NC>(rig, raw, xh, v, u, X0, Y0, Z0);
+            if (lane == 0 && e0 < l_err) l_err = e0, l_d = 0, lx = X0, ly = Y0, lz = Z0, l_have = true;
+          }
           dcur = cert_advance<NC>(v, cert_next(v, 0u), badrow, min_cams);
           if (dcur != 0) continue;
         }
@@ -685,13 +843,18 @@ k_cert_overflow(const __grid_constant__ RigDev rig, const uint32_t* __restrict__
       int ne = 1;
       if (ran_out) ne += count_adm(cumb, (1u << k) - 1u, k - min_cams);
       else ne += count_adm(cumb, s_sel, k - min_cams);
-      RansacSlot* sl = slots + idx;
-      sl->best_err = best_err;
-      sl->bx = bx;
-      sl->by = by;
-      sl->bz = bz;
-      sl->best_s = have ? (int32_t)s_sel : -1;
-      sl->neval = ne;
+      if (outs.p3d) {
+        cert_write_point<NC>(outs, C, idx, v, best_d, have, best_err, bx, by, bz, (int32_t)s_sel, ne, raw);
+      } else {
+        RansacSlot* sl = slots + idx;
+        sl->best_err = best_err;
+        sl->bx = bx;
+        sl->by = by;
+        sl->bz = bz;
+        sl->masks = __brev(v) >> (32 - C);
+        sl->best_s = have ? (int32_t)s_sel : -1;
+        sl->neval = ne;
+      }
     }
   }
 }
