@@ -362,7 +362,7 @@ def test_gpu_baseline_full_size_properties():
     cams = fixtures.cams_from_dicts(dicts)
     cg = CameraGroup.from_dicts(dicts)
     dev = torch.device("cuda", torch.cuda.current_device())
-    _, xy = make_device_workload(cg, 1000000, 4, 17, seed, "dlt", dev)
+    xy = make_device_workload(cg, 1000000, 4, 17, seed, "dlt", dev)
     n = xy.shape[1]
     assert n == 68000000
     p3d, err = cg.triangulate_with_error(xy)
@@ -387,7 +387,7 @@ def test_gpu_baseline_full_size_properties():
     del xy, p3d, err, nvalid
     torch.cuda.empty_cache()
 
-    _, xy = make_device_workload(cg, 200000, 4, 17, seed, "ransac", dev)
+    xy = make_device_workload(cg, 200000, 4, 17, seed, "ransac", dev)
     n = xy.shape[1]
     out, picked, xyp, rerr, sidx, nev = cg.triangulate_ransac(xy, return_stats=True)
     idx = np.sort(rng.choice(n, 3000, replace=False))
