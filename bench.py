@@ -678,41 +678,81 @@ def measure(cx, args, workload):
             off += n
         assert off == N
         nev = torch.empty((N,), dtype=torch.int32, device=device)
+        # delivery of p3d + err to rank 0 (sharding.py): "peer" = every rank's copy engine writes its
+        # finished tile into rank 0's window over NVLink (the headline), "direct" = the search kernels
+        # store into the window themselves, "gather" = one NCCL gather per round, "none" = no exchange
+        pr = sharding.PeerResults(plan, [(3,), ()], torch.float64, device, dst=0, group=None) if world > 1 else None
         rg = sharding.RoundGather(plan, [(3,), ()], torch.float64, device, dst=0, group=None) if world > 1 else None
+        mode = ["peer" if world > 1 else "none"]
+        if pr is not None and rank == 0:
+            for w in pr.out:
+                w.fill_(float("nan"))
 
         def step():
+            m = mode[0]
             for j, t in enumerate(tiles):
                 o, n = t["off"], t["n"]
+                p3d_ptr, err_ptr = p3d[o:o + n].data_ptr(), err[o:o + n].data_ptr()
+                direct = m == "direct" or (m == "peer" and rank == 0)
+                if direct:
+                    p3d_ptr, err_ptr = pr.row_ptrs(j)
                 if n:
                     _lib.check(lib.m3d_triangulate_ransac(
-                        rig.handle, t["xy"].data_ptr(), n, 1, 2, 0.5, 200.0, p3d[o:o + n].data_ptr(),
-                        t["picked"].data_ptr(), t["xyp"].data_ptr(), err[o:o + n].data_ptr(), None,
+                        rig.handle, t["xy"].data_ptr(), n, 1, 2, 0.5, 200.0, p3d_ptr,
+                        t["picked"].data_ptr(), t["xyp"].data_ptr(), err_ptr, None,
                         nev[o:o + n].data_ptr(), cx.stream.cuda_stream), "bench step")
-                if rg is not None:
+                if m == "gather":
                     rg.add(j, [p3d[o:o + n], err[o:o + n]])
-            if rg is not None:
+                elif m == "peer" and not direct:
+                    pr.push(j, [p3d[o:o + n], err[o:o + n]])
+            if m == "gather":
                 rg.finish()
+            elif m in ("peer", "direct"):
+                pr.finish()
         collective = None if world == 1 else {
-            "what": "torch.distributed.gather (NCCL, async_op) of p3d + err to rank 0, one per tile round, issued "
-                    "inside the timed step and overlapped with the next round's kernels; rank 0 receives in "
-                    "global frame order", "rounds_per_step": plan.rounds,
-            "bytes_to_rank0_per_step": int((world - 1) * N * 32)}
+            "what": "p3d + err of every tile delivered to rank 0's frame-ordered arrays INSIDE the timed step: each "
+                    "rank's copy engine writes its finished tile into rank 0's CUDA-IPC window over NVLink "
+                    "(m3d_peer_push) while the next tile's kernels run; one 4-byte NCCL all-reduce ends the step",
+            "rounds_per_step": plan.rounds, "bytes_to_rank0_per_step": int((world - 1) * N * 32)}
 
     ms_per_step, launches = timed_steps(cx, step, args.steps, args.warmup)
     value = world * N / (ms_per_step * 1e-3)
     if workload == "ransac" and world > 1:
-        # the same step without the collective: what the gather costs
-        rg_keep = rg
-        rg = None
-        ms_nc, _ = timed_steps(cx, step, max(2, args.steps // 2), 3)
-        rg = rg_keep
-        collective["ms_per_step_without_collective"] = ms_nc
-        collective["ms_per_step_with_collective"] = ms_per_step
-        if rank == 0:   # sharded result == this rank's own tiles where they land in the global arrays
-            res = rg.out
-            j, t = 0, tiles[0]
+        def window_check(tag):
+            # the delivered rows == this rank's own tiles, wherever rank 0 can see both
+            torch.cuda.synchronize()
+            if rank == 0:       # err is never NaN (cameras.py:675) and the window was NaN-filled: every row arrived
+                assert bool(torch.isfinite(pr.out[1]).all()), tag + ": rows missing"
+            # every rank: its first tile as delivered, compared on rank 0 with the rank's own copy
+            j = 0
             a, b = plan.tile_span(j * world + rank)
-            assert torch.equal(res[1][a * per:b * per], err[t["off"]:t["off"] + t["n"]]), "gathered rows differ"
+            got = [torch.empty(((b - a) * per,), dtype=torch.float64, device=device) for _ in range(world)] \
+                if rank == 0 else None
+            t = tiles[j]
+            mine = err[t["off"]:t["off"] + t["n"]].contiguous()
+            dist_ = torch.distributed
+            dist_.gather(mine, got, dst=0)
+            if rank == 0:
+                for r in range(1, world):
+                    a, b = plan.tile_span(j * world + r)
+                    assert torch.equal(pr.out[1][a * per:b * per], got[r]), tag + ": delivered rows differ"
+        window_check("peer")
+        collective["ms_per_step_with_exchange"] = ms_per_step
+        # the same step with the alternatives, and with no exchange at all: what the delivery costs
+        for m, key in (("none", "ms_per_step_without_exchange"), ("gather", "ms_per_step_nccl_gather_per_round"),
+                       ("direct", "ms_per_step_kernel_stores_into_window")):
+            mode[0] = m
+            if m == "direct" and rank == 0:
+                pr.out[1].fill_(float("nan"))
+            sync_all(cx)
+            collective[key], _ = timed_steps(cx, step, max(3, args.steps // 2), 3)
+            if m == "direct":
+                window_check("direct")
+            if m == "gather" and rank == 0:
+                t = tiles[0]
+                a, b = plan.tile_span(rank)
+                assert torch.equal(rg.out[1][a * per:b * per], err[t["off"]:t["off"] + t["n"]]), "gathered rows differ"
+        mode[0] = "peer"
     kernels = kernel_breakdown(cx, step) if rank == 0 or world > 1 else {}
     if workload == "dlt":
         # the opt-in north-star-tolerance path (first three undistortion iterations in float32)
@@ -755,6 +795,8 @@ def measure(cx, args, workload):
             out["e2e"] = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:300]}
     out["config"] = config_dict(workload, C, F, world)
     out["extra"] = extra
+    if workload == "ransac" and pr is not None:
+        pr.close()
     del xy, p3d, err
     torch.cuda.empty_cache()
     return out

@@ -35,6 +35,7 @@ extern "C" {
 #define M3D_MAX_CAMS 16
 #define M3D_MAX_JOINTS 32   /* keypoints per detection in m3d_ray_affinity */
 #define M3D_MAX_DETS 128    /* detections per frame in m3d_ray_affinity */
+#define M3D_PEER_HANDLE_BYTES 64 /* size of the window handle of m3d_peer_alloc (a CUDA IPC memory handle) */
 #define M3D_MAX_DETS_SVT 112 /* detections per frame in m3d_match_svt (shared-memory limit of its Jacobi SVD) */
 
 #define M3D_OK 0
@@ -278,6 +279,25 @@ int m3d_optim_points(const m3d_rig* rig, const double* p2d_dev, const double* sc
                      double reproj_error_threshold, int32_t loss, int32_t n_deriv_smooth,
                      int32_t fix_lengths, double ftol, int32_t max_iter, int32_t mode,
                      double* params_dev, double* out_dev, double* info_host, void* stream);
+
+/* ---- multi-GPU result window ---------------------------------------- */
+/* The reference is one NumPy process (cameras.py:639-743 returns one array for the whole recording);
+ * the frame-sharded run keeps that contract by letting ONE rank own the frame-ordered result arrays
+ * and every other rank (one process per GPU) write its finished tiles straight into them over
+ * NVLink with its copy engine - no gather collective, no SM on either side.
+ *   m3d_peer_alloc   owner: cudaMalloc `bytes` on `device`, export the M3D_PEER_HANDLE_BYTES handle
+ *                    (send it to the other ranks by any means, e.g. torch.distributed object broadcast)
+ *   m3d_peer_open    other ranks: map the owner's allocation for use from `device` (peer access to the
+ *                    owner's GPU is enabled on demand); the pointer is valid for kernels and copies
+ *   m3d_peer_push    asynchronous device-to-device copy of `bytes` into the window, ordered on `stream`
+ *   m3d_peer_close / m3d_peer_free   unmap / release
+ * Completion is the caller's: order a collective (or any cross-rank signal) after the pushes of every
+ * rank before the owner reads (sharding.PeerResults.finish). */
+int m3d_peer_alloc(int32_t device, int64_t bytes, void** dptr_out, uint8_t* handle_out);
+int m3d_peer_open(int32_t device, const uint8_t* handle, void** dptr_out);
+int m3d_peer_push(void* dst_window, const void* src_dev, int64_t bytes, void* stream);
+int m3d_peer_close(int32_t device, void* dptr);
+int m3d_peer_free(int32_t device, void* dptr);
 
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Number of kernels this library has launched on the calling process (bench.py's

@@ -6,13 +6,22 @@ to rank t % world): the per-point cost of the subset RANSAC is heavy-tailed and 
 (occlusions), so interleaving balances the ranks, and one ROUND (one tile of every rank) is a
 contiguous block of ``world`` tiles of the recording.
 
-The only collective is the gather of the 3D results (p3d + err = 32 B per joint-instance) to one
-rank.  It is issued PER ROUND, asynchronously (``async_op=True``: NCCL's own stream), straight into
-the destination's frame-ordered result arrays (round j lands at rows [j * world * tile, ...) — no
-reorder pass), while the next round's kernels run; the step ends when the last gather has landed.
-Works with any ``torch.distributed`` backend (NCCL over NVLink on the B200 box, gloo in the CPU
-tests).  A rank only ever holds the observations of its own tiles.
+The only exchange is the delivery of the 3D results (p3d + err = 32 B per joint-instance) to one
+rank, into frame-ordered arrays of the whole recording (round j lands at rows [j * world * tile, ...)
+— no reorder pass).  Two implementations:
+
+* ``PeerResults`` (NCCL runs, the default on the B200 box): the destination rank's arrays are a
+  CUDA IPC window every other rank maps over NVLink peer access; a rank's COPY ENGINE writes each
+  finished tile straight to its rows while the next tile's kernels run.  No SM takes part, no rank
+  waits for another per tile; one tiny all-reduce at the end of the step orders the destination
+  behind everybody's last copy.
+* ``RoundGather`` (any ``torch.distributed`` backend; gloo in the CPU tests): one asynchronous
+  ``dist.gather`` per round, received in place.
+
+A rank only ever holds the observations of its own tiles.
 """
+import ctypes
+
 import numpy as np
 
 try:
@@ -154,8 +163,112 @@ class RoundGather:
         return self.out
 
 
+class _DeviceBytes:
+    """A raw device allocation as seen by ``torch.as_tensor`` (the CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerResults:
+    """Frame-ordered result arrays of the whole recording on rank ``dst``, written by every rank's
+    copy engine through a peer-mapped window (``m3d_peer_*``, csrc/m3d_peer.cu).
+
+    ``push(j, tensors)`` is called by every rank after it has queued the kernels of round j; the
+    copies run on a side stream behind those kernels.  ``row_ptrs(j)`` gives the window addresses of this
+    rank's tile of round j (the kernels of ``dst`` write them directly instead of pushing).  ``finish()`` orders the calling stream behind the pushes of ALL ranks and returns the
+    global arrays on ``dst`` (None elsewhere).  NCCL only: the window is device memory."""
+
+    def __init__(self, plan, row_shapes, dtype, device, dst=0, group=None):
+        from . import _lib
+        self.lib = _lib.require_gpu()
+        self._check = _lib.check
+        self.plan, self.group, self.dst = plan, group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dtype = dtype
+        self.row_shapes = [tuple(s) for s in row_shapes]
+        item = torch.empty((), dtype=dtype).element_size()
+        total = plan.n_frames * plan.per
+        self.row_bytes = [item * int(np.prod(s, dtype=np.int64)) for s in self.row_shapes]
+        self.offsets, off = [], 0
+        for rb in self.row_bytes:                      # 256-byte aligned sections of ONE allocation
+            self.offsets.append(off)
+            off += -(-(total * rb) // 256) * 256
+        self.nbytes = max(off, 256)
+        self.base = ctypes.c_void_p()
+        self.owner = self.rank == dst
+        handle = [None]
+        if self.owner:
+            buf = (ctypes.c_uint8 * 64)()
+            self._check(self.lib.m3d_peer_alloc(self.dev_index, self.nbytes, ctypes.byref(self.base), buf),
+                        "m3d_peer_alloc")
+            handle[0] = bytes(buf)
+        dist.broadcast_object_list(handle, src=dist.get_global_rank(group, dst) if group is not None else dst,
+                                   group=group)
+        if not self.owner:
+            buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle[0])
+            self._check(self.lib.m3d_peer_open(self.dev_index, buf, ctypes.byref(self.base)), "m3d_peer_open")
+        # the window as tensors: on the owner only (elsewhere the mapping is used through raw pointers, so
+        # that torch never has to decide which device an IPC mapping belongs to)
+        self.window = None
+        if self.owner:
+            raw = torch.as_tensor(_DeviceBytes(self.base.value, self.nbytes), device=self.device)
+            self.window = [raw[o:o + total * rb].view(dtype).view((total,) + s)
+                           for o, rb, s in zip(self.offsets, self.row_bytes, self.row_shapes)]
+        self.out = self.window
+        self.side = torch.cuda.Stream(self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._keep = []
+
+    def row_ptrs(self, j, rank=None):
+        """Device pointers (valid on THIS rank) of the window rows of the tile of ``rank`` (default: this
+        rank) in round j, one per result array: a kernel may write its results there directly."""
+        r = self.rank if rank is None else rank
+        a, _ = self.plan.tile_span(j * self.world + r)
+        return [self.base.value + o + a * self.plan.per * rb for o, rb in zip(self.offsets, self.row_bytes)]
+
+    def push(self, j, tensors):
+        a, b = self.plan.tile_span(j * self.world + self.rank)
+        rows = (b - a) * self.plan.per
+        if rows == 0 or tensors is None:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)                     # behind the kernels that produce the tile
+        for k, rb in enumerate(self.row_bytes):
+            t = tensors[k]
+            assert t.shape[0] == rows and t.is_contiguous() and t.dtype == self.dtype
+            self._keep.append(t)                       # alive until finish()
+            self._check(self.lib.m3d_peer_push(self.base.value + self.offsets[k] + a * self.plan.per * rb,
+                                               t.data_ptr(), rows * rb, self.side.cuda_stream), "m3d_peer_push")
+
+    def finish(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.side)
+        # every rank contributes after its own last copy: on return the calling stream of `dst` is
+        # ordered behind the copies (and direct window writes) of all ranks
+        dist.all_reduce(self._flag, group=self.group)
+        self._keep = []
+        return self.out
+
+    def close(self):
+        if self.base is not None and self.base.value:
+            torch.cuda.synchronize(self.device)
+            self.window = self.out = None
+            if self.owner:
+                dist.barrier(group=self.group)         # nobody writes any more
+                self.lib.m3d_peer_free(self.dev_index, self.base)
+            else:
+                self.lib.m3d_peer_close(self.dev_index, self.base)
+                dist.barrier(group=self.group)
+            self.base = ctypes.c_void_p()
+
+
 def triangulate_sharded(cgroup, local_points, n_frames, ransac=False, min_cams=2, gather=True, group=None,
-                        tile_frames="auto"):
+                        tile_frames="auto", exchange="auto"):
     """Run this rank's frames through the GPU CameraGroup and gather (p3d, err) to rank 0.
 
     ``local_points`` (C, n_local, 2): the observations of THIS rank's frames only, in the order of
@@ -163,7 +276,9 @@ def triangulate_sharded(cgroup, local_points, n_frames, ransac=False, min_cams=2
     ``n_frames``: frames of the whole recording.  ``tile_frames``: an int = tile size of the
     round-robin deal; "auto" = about 16 tiles per rank (at least RANSAC_TILE_FRAMES frames each) for the
     subset RANSAC and one even split per rank for the DLT path.  Returns (p3d, err) of the whole recording in frame order on rank 0, (None,
-    None) on the other ranks; with ``gather=False`` every rank gets its local results."""
+    None) on the other ranks; with ``gather=False`` every rank gets its local results.
+    ``exchange``: "peer" = ``PeerResults`` (copy-engine writes into rank 0's window over NVLink; NCCL
+    runs only), "gather" = ``RoundGather`` (one ``dist.gather`` per round), "auto" = "peer" under NCCL."""
     world = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     per_guess = 0
@@ -206,6 +321,26 @@ def triangulate_sharded(cgroup, local_points, n_frames, ransac=False, min_cams=2
     as_numpy = isinstance(local_points, np.ndarray)
     backend = dist.get_backend(group)
     device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if exchange == "auto":
+        exchange = "peer" if backend == "nccl" else "gather"
+    assert exchange in ("peer", "gather") and (exchange == "gather" or backend == "nccl"), \
+        "the peer window needs device memory (NCCL runs)"
+    if exchange == "peer":
+        pr = PeerResults(plan, [(3,), ()], torch.float64, device, dst=0, group=group)
+        for j in range(plan.rounds):
+            a, b = plan.tile_span(j * world + rank)
+            if b > a:
+                off = plan.local_offset(rank, j)
+                p3d, err = run(local_points[:, off:off + (b - a) * plan.per])
+                pr.push(j, [torch.as_tensor(p3d).to(device).contiguous(), torch.as_tensor(err).to(device).contiguous()])
+        out = pr.finish()
+        res = (None, None)
+        if rank == 0:
+            res = (out[0].clone(), out[1].clone())     # the window is released below
+        pr.close()
+        if rank == 0 and as_numpy:
+            return res[0].cpu().numpy(), res[1].cpu().numpy()
+        return res
     rg = RoundGather(plan, [(3,), ()], torch.float64, device, dst=0, group=group)
     for j in range(plan.rounds):
         a, b = plan.tile_span(j * world + rank)

@@ -1,6 +1,6 @@
-"""GPU tier, N > 1: the frame-sharded subset RANSAC over NCCL (one process per GPU, round-robin
-tiles, per-round gather into rank 0's frame-ordered arrays) returns bit-for-bit what one GPU returns
-for the whole recording.  Needs two visible GPUs (the driver's single-GPU box skips it; run with
+"""GPU tier, N > 1: the frame-sharded subset RANSAC (one process per GPU, round-robin tiles, results
+delivered into rank 0's frame-ordered arrays — by copy-engine writes into its peer window over NVLink,
+or by a per-round NCCL gather) returns bit-for-bit what one GPU returns for the whole recording.  Needs two visible GPUs (the driver's single-GPU box skips it; run with
 `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`)."""
 import os
 import socket
@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_frames, tile, ransac, tmp):
+def _worker(rank, world, port, n_frames, tile, ransac, exchange, tmp):
     import torch
     import torch.distributed as dist
     from macaque_3d_pose_estimation_b200 import sharding, synth
@@ -42,7 +42,7 @@ def _worker(rank, world, port, n_frames, tile, ransac, tmp):
             even = max(1, -(-n_frames // world))
             tl = max(sharding.RANSAC_TILE_FRAMES, -(-even // 16)) if ransac else even
         local = torch.from_numpy(np.ascontiguousarray(sharding.shard_points(p2, n_frames, rank, world, tl))).cuda()
-        p3d, err = sharding.triangulate_sharded(cg, local, n_frames, ransac=ransac, tile_frames=tile)
+        p3d, err = sharding.triangulate_sharded(cg, local, n_frames, ransac=ransac, tile_frames=tile, exchange=exchange)
         if rank == 0:
             full = torch.from_numpy(p2).cuda()
             if ransac:
@@ -57,8 +57,10 @@ def _worker(rank, world, port, n_frames, tile, ransac, tmp):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,tile,ransac", [(3000, 97, True), (700, "auto", True), (1000, "auto", False), (5, 256, True)])
-def test_nccl_sharded_equals_single_gpu(tmp_path, n_frames, tile, ransac):
+@pytest.mark.parametrize("exchange", ["peer", "gather"])
+@pytest.mark.parametrize("n_frames,tile,ransac", [(3000, 97, True), (700, "auto", True), (1000, "auto", False), (5, 256, True),
+                                                  (1, 256, True)])
+def test_nccl_sharded_equals_single_gpu(tmp_path, n_frames, tile, ransac, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -67,7 +69,7 @@ def test_nccl_sharded_equals_single_gpu(tmp_path, n_frames, tile, ransac):
     import __graft_entry__ as ge
     ge.build_library()
     tmp = str(tmp_path / "out.npz")
-    mp.spawn(_worker, args=(2, _free_port(), n_frames, tile, ransac, tmp), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_frames, tile, ransac, exchange, tmp), nprocs=2, join=True)
     r = np.load(tmp)
     assert r["n"] == n_frames * 34
     assert bool(r["ok3"]) and bool(r["oke"]), "sharded result differs from the single-GPU result"
