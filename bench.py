@@ -328,10 +328,11 @@ def cfg4_line(cx, args):
         cid = np.where(rng.random((F, M)) < 0.6, owner, -1).astype(np.int32)
         chunk = 10000
         crossview.associate_batch(cx.cg, kp[:2000], dim[:2000], cid[:2000])              # warm-up
+        stages = {}
         t0 = time.perf_counter()
         n_person, ok = 0, 0
         for a in range(0, F, chunk):
-            res = crossview.associate_batch(cx.cg, kp[a:a + chunk], dim[a:a + chunk], cid[a:a + chunk])
+            res = crossview.associate_batch(cx.cg, kp[a:a + chunk], dim[a:a + chunk], cid[a:a + chunk], timing=stages)
             n_person += len(res["frame"])
             mem = res["members"]
             own = np.where(mem >= 0, owner[0][np.where(mem >= 0, mem, 0)], -1)
@@ -342,7 +343,20 @@ def cfg4_line(cx, args):
                            "views (M = %d detections per keyframe), %d keyframes" % (C, M, F),
                "value": F / dt, "unit": "keyframes/s (one GPU, host arrays in and out)", "seconds": dt,
                "joint_instances_per_s": F * A * J / dt, "persons_found_per_frame": n_person / F,
-               "pure_clusters_fraction": ok / max(1, n_person)}
+               "pure_clusters_fraction": ok / max(1, n_person),
+               "stages_s": {k: round(v, 4) for k, v in stages.items()}}
+        # the same with the detections already on the device (what a GPU pose network upstream would hand over)
+        import torch
+        nd = min(F, 2 * chunk)
+        d_kp = torch.from_numpy(kp[:nd]).to(cx.device)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a in range(0, nd, chunk):
+            crossview.associate_batch(cx.cg, d_kp[a:a + chunk], dim[a:a + chunk], cid[a:a + chunk])
+        torch.cuda.synchronize()
+        out["device_resident_input"] = {"value": nd / (time.perf_counter() - t0), "unit": "keyframes/s",
+                                        "keyframes": nd}
+        del d_kp
         if not args.no_cpu:
             from oracle import crossview as ocv
             from oracle import fixtures

@@ -280,6 +280,28 @@ int m3d_optim_points(const m3d_rig* rig, const double* p2d_dev, const double* sc
                      int32_t fix_lengths, double ftol, int32_t max_iter, int32_t mode,
                      double* params_dev, double* out_dev, double* info_host, void* stream);
 
+/* Batched keyframe association (crossview.associate_batch): the device stages around the kernels above.
+ *   m3d_undistort_detections   kp_raw_dev (F,M,J,3) raw pixels + score -> kp_und_dev (F,M,J,3) undistorted
+ *                              x, y (NaN in padding slots) + score; the camera of a slot follows from
+ *                              dim_dev (F,C+1) (step2_crossviewmatching.py:306-325, 520-530)
+ *   m3d_cluster_members        label_dev (F,M) from m3d_match_clusters -> persons as member tables
+ *                              (step2:598-607, 697-698).  Pass 1 (offsets_dev NULL): count_dev (F) persons per
+ *                              frame, dup_dev (F) u8 = 1 where a cluster holds two detections of one camera
+ *                              (count 0: the caller resolves such frames, step2:610-657).  Pass 2 (offsets_dev
+ *                              (F) i64 = exclusive prefix sums of count): frame_dev (P), column_dev (P),
+ *                              members_dev (P,C) detection index per camera or -1, in (frame, column) order
+ *   m3d_triangulate_ls_members calc_3dpose (step2:436-461) of P persons: camera c contributes keypoint j of
+ *                              detection members[p][c] of frame[p] when x is not NaN and score >= thr_kp;
+ *                              p3d_dev (P,J,3), NaN with fewer than two contributing cameras */
+int m3d_undistort_detections(const m3d_rig* rig, const double* kp_raw_dev, const int32_t* dim_dev, int64_t F,
+                             int32_t M, int32_t J, double* kp_und_dev, void* stream);
+int m3d_cluster_members(const int32_t* label_dev, const int32_t* dim_dev, int32_t F, int32_t M, int32_t C,
+                        const int64_t* offsets_dev, int32_t* count_dev, uint8_t* dup_dev, int32_t* frame_dev,
+                        int32_t* column_dev, int32_t* members_dev, int32_t device, void* stream);
+int m3d_triangulate_ls_members(const m3d_rig* rig, const double* kp_und_dev, const int32_t* frame_dev,
+                               const int32_t* members_dev, int64_t P, int32_t M, int32_t J, double thr_kp,
+                               double* p3d_dev, void* stream);
+
 /* ---- multi-GPU result window ---------------------------------------- */
 /* The reference is one NumPy process (cameras.py:639-743 returns one array for the whole recording);
  * the frame-sharded run keeps that contract by letting ONE rank own the frame-ordered result arrays

@@ -75,6 +75,9 @@ SIGNATURES = {
     "m3d_viterbi_filter": (ctypes.c_int, [_P, _L, _L, _I, _I, _D, _D, _D, _P, _P, _I, _P]),
     "m3d_optim_points": (ctypes.c_int, [_P, _P, _P, _I, _I, _P, _I, _P, _I, _D, _D, _D, _D, _I, _I, _I, _D, _I, _I,
                                         _P, _P, _P, _P]),
+    "m3d_undistort_detections": (ctypes.c_int, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "m3d_cluster_members": (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "m3d_triangulate_ls_members": (ctypes.c_int, [_P, _P, _P, _P, _L, _I, _I, _D, _P, _P]),
     "m3d_peer_alloc": (ctypes.c_int, [_I, _L, ctypes.POINTER(_P), _P]),
     "m3d_peer_open": (ctypes.c_int, [_I, _P, ctypes.POINTER(_P)]),
     "m3d_peer_push": (ctypes.c_int, [_P, _P, _L, _P]),

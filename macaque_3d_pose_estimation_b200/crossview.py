@@ -209,18 +209,6 @@ def _cam_of(dim, M):
     return (np.arange(M)[None, :, None] >= dim[:, None, 1:]).sum(axis=2)
 
 
-def _undistort_detections(cgroup, kp_raw, cam_of, n_cams):
-    """Undistort the keypoints of all detections of all frames, one launch per camera."""
-    F, M, J, _ = kp_raw.shape
-    und = np.full((F, M, J, 2), np.nan)
-    for c in range(n_cams):
-        sel = cam_of == c
-        if sel.any():
-            pts = np.ascontiguousarray(kp_raw[sel][:, :, :2])                      # (n, J, 2)
-            und[sel] = cgroup.cameras[c].undistort_points(pts.reshape(1, -1, 2)).reshape(-1, J, 2)
-    return und
-
-
 def _ls_persons(cgroup, und_sel, score_sel, thr_kp):
     """und_sel (P, C, J, 2), score_sel (P, C, J) -> (P, J, 3): calc_3dpose (step2:436-461) for P persons in
     one launch (a camera without a member has score 0 everywhere)."""
@@ -244,52 +232,15 @@ def _combo_rmse(cgroup, kp_raw_sel, p3d, thr_kp):
         return np.where(n > 0, np.sqrt(np.where(keep, d2, 0.0).sum(axis=(1, 2)) / np.maximum(n, 1)), np.inf)
 
 
-def associate_batch(cgroup, kp_raw, dim, cid=None, bbox_id=None, thr_kp=THR_KP, alpha_id=0.2, alpha_svt=0.5,
-                    lambda_svt=50.0):
-    """Cross-view association + reconstruction of F keyframes at once — what
-    MultiEstimator.predict_data (step2_crossviewmatching.py:502-713) does per keyframe.
-
-      kp_raw (F, M, J, 3)  raw pixels + score of every detection, grouped by camera (padding beyond dim[:, C])
-      dim    (F, C+1)      cumulative detection counts per camera (dimGroup)
-      cid    (F, M) int    identity label per detection or -1 (None: no identity term)
-      bbox_id (F, M) int   tracklet id reported back per person and camera (None: the detection index)
-
-    Device stages (all frames per launch): undistortion, ray affinity, association weights, SVT matching,
-    cluster labels, least-squares triangulation, reprojection scoring of the duplicate combinations.  The
-    host only resolves clusters with two detections from one camera (rare) — by scoring ALL candidate
-    combinations of all frames in one batch.
-
-    Returns {'label' (F,M) person column per detection or -1, 'frame' (P,), 'members' (P,C) detection index
-    per camera or -1, 'p3d' (P,J,3), 'bcomb' (P,C)}; persons are ordered by frame, then like the reference
-    (ascending cluster column; a cluster's leftover combination follows its best one)."""
+def _resolve_duplicate_frames(cgroup, frames, label, cam_of, kp_raw, und, thr_kp):
+    """Host resolution of the keyframes in which a cluster holds two detections of one camera
+    (get_best_comb, step2_crossviewmatching.py:610-657): all candidate combinations of all such clusters are
+    scored in one batch (LS triangulation + reprojection RMSE), then the leftover round.  ``label`` /
+    ``cam_of`` / ``kp_raw`` / ``und`` are the rows of ``frames`` only.  Returns [(frame, (column, 0 | 1),
+    member row)] for every cluster of these frames."""
     import itertools
-    kp_raw = np.asarray(kp_raw, dtype=np.float64)
-    dim = np.ascontiguousarray(dim, dtype=np.int32)
-    F, M, J, _ = kp_raw.shape
+    n, M = label.shape
     C = len(cgroup.cameras)
-    assert dim.shape == (F, C + 1)
-    device = cgroup._dev()
-    lib = _lib.require_gpu()
-    cam_of = _cam_of(dim, M)
-    und = _undistort_detections(cgroup, kp_raw, cam_of, C)
-    kp_und = np.concatenate([und, kp_raw[..., 2:3]], axis=-1)
-    dev = "cuda:%d" % device
-    aff = geometry_affinity_batch(cgroup, torch.from_numpy(np.nan_to_num(kp_und)).to(dev), dim, thr_kp)
-    d_dim = torch.from_numpy(dim).to(dev)
-    ids = np.full((F, M), -1, dtype=np.int32) if cid is None else np.ascontiguousarray(cid, dtype=np.int32)
-    d_cid = torch.from_numpy(ids).to(dev)
-    W = torch.empty_like(aff)
-    _lib.check(lib.m3d_association_weights(_ptr(aff), ctypes.c_void_p(d_cid.data_ptr()),
-                                           ctypes.c_void_p(d_dim.data_ptr()), F, M, C, float(alpha_id), _ptr(W),
-                                           int(device), _stream(device)), "m3d_association_weights")
-    match = match_svt_batch(W, d_dim, C, alpha=alpha_svt, _lambda=lambda_svt, device=device)
-    label = torch.empty((F, M), dtype=torch.int32, device=dev)
-    _lib.check(lib.m3d_match_clusters(ctypes.c_void_p(match.data_ptr()), ctypes.c_void_p(d_dim.data_ptr()), F, M, C,
-                                      ctypes.c_void_p(label.data_ptr()), int(device), _stream(device)),
-               "m3d_match_clusters")
-    label = label.cpu().numpy()
-
-    # ---- clusters -> one detection per camera (host bookkeeping on (F, M) integers) -----------------
     fi, mi = np.nonzero(label >= 0)
     key = fi.astype(np.int64) * M + label[fi, mi]
     order = np.lexsort((mi, key))
@@ -297,7 +248,6 @@ def associate_batch(cgroup, kp_raw, dim, cid=None, bbox_id=None, thr_kp=THR_KP, 
     ci = cam_of[fi, mi]
     ukey, start = np.unique(key, return_index=True)
     cnt = np.diff(np.append(start, key.size))
-    # members table (cluster, camera) -> detection, -1 = none, -2 = several
     members = -np.ones((ukey.size, C), dtype=np.int64)
     cl = np.repeat(np.arange(ukey.size), cnt)
     first = np.ones(key.size, dtype=bool)
@@ -305,65 +255,164 @@ def associate_batch(cgroup, kp_raw, dim, cid=None, bbox_id=None, thr_kp=THR_KP, 
     first[1:] = pair[1:] != pair[:-1]
     members[cl[first], ci[first]] = mi[first]
     dup_clusters = np.unique(cl[~first])
-    persons = []                                      # (frame, sort key, member row)
-    clean = np.setdiff1d(np.arange(ukey.size), dup_clusters)
-    for k in clean:
-        persons.append((int(ukey[k] // M), (int(ukey[k] % M), 0), members[k]))
+    persons = []
+    for k in np.setdiff1d(np.arange(ukey.size), dup_clusters):
+        persons.append((int(frames[ukey[k] // M]), (int(ukey[k] % M), 0), members[k]))
+
+    def score_round(groups):
+        combos, owner = [], []
+        for gi, (f, dets) in enumerate(groups):
+            per_cam = [[m for m in dets if cam_of[f, m] == c] or [-1] for c in range(C)]
+            for combo in itertools.product(*per_cam):
+                combos.append(combo)
+                owner.append(gi)
+        combos = np.array(combos, dtype=np.int64)
+        owner = np.array(owner)
+        fr = np.array([groups[g][0] for g in owner])
+        has = combos >= 0
+        safe = np.where(has, combos, 0)
+        raw_sel = kp_raw[fr[:, None], safe] * has[..., None, None]
+        und_sel = np.where(has[..., None, None], und[fr[:, None], safe], 0.0)
+        p3d = _ls_persons(cgroup, und_sel, raw_sel[..., 2], thr_kp)
+        err = _combo_rmse(cgroup, raw_sel, p3d, thr_kp)
+        best = []
+        for gi in range(len(groups)):
+            idx = np.nonzero(owner == gi)[0]
+            best.append(combos[idx[int(np.argmin(err[idx]))]])              # first minimum, like np.argmin
+        return best
+
     if dup_clusters.size:
-        # every combination of every ambiguous cluster, scored in one batch (get_best_comb, step2:610-646)
-        def score_round(groups):
-            combos, owner = [], []
-            for gi, (f, dets) in enumerate(groups):
-                per_cam = [[m for m in dets if cam_of[f, m] == c] or [-1] for c in range(C)]
-                for combo in itertools.product(*per_cam):
-                    combos.append(combo)
-                    owner.append(gi)
-            combos = np.array(combos, dtype=np.int64)
-            owner = np.array(owner)
-            fr = np.array([groups[g][0] for g in owner])
-            has = combos >= 0
-            safe = np.where(has, combos, 0)
-            raw_sel = kp_raw[fr[:, None], safe] * has[..., None, None]
-            und_sel = np.where(has[..., None, None], und[fr[:, None], safe], 0.0)
-            p3d = _ls_persons(cgroup, und_sel, raw_sel[..., 2], thr_kp)
-            err = _combo_rmse(cgroup, raw_sel, p3d, thr_kp)
-            best = []
-            for gi in range(len(groups)):
-                idx = np.nonzero(owner == gi)[0]
-                best.append(combos[idx[int(np.argmin(err[idx]))]])          # first minimum, like np.argmin
-            return best
-        groups = []
-        for k in dup_clusters:
-            f = int(ukey[k] // M)
-            groups.append((f, mi[cl == k].tolist()))
+        groups = [(int(ukey[k] // M), mi[cl == k].tolist()) for k in dup_clusters]
         best = score_round(groups)
         left_groups, left_of = [], []
         for gi, k in enumerate(dup_clusters):
             f, dets = groups[gi]
-            persons.append((f, (int(ukey[k] % M), 0), best[gi]))
+            persons.append((int(frames[f]), (int(ukey[k] % M), 0), best[gi]))
             rest = sorted(set(dets) - set(int(m) for m in best[gi] if m >= 0))
             if len(rest) > 1:                                               # step2:653-657
                 left_groups.append((f, rest))
                 left_of.append(k)
         if left_groups:
             # a leftover group with one detection per camera is taken as is, otherwise scored again
-            best2 = score_round(left_groups)
-            for (f, rest), k, b in zip(left_groups, left_of, best2):
-                persons.append((f, (int(ukey[k] % M), 1), b))
-    persons = [p for p in persons if (p[2] >= 0).sum() >= 2]                # step2:697-698
-    persons.sort(key=lambda p: (p[0], p[1]))
-    P = len(persons)
-    frame = np.array([p[0] for p in persons], dtype=np.int64)
-    mem = np.array([p[2] for p in persons], dtype=np.int64).reshape(P, C)
-    has = mem >= 0
-    safe = np.where(has, mem, 0)
-    if P:
-        und_sel = np.where(has[..., None, None], und[frame[:, None], safe], 0.0)
-        sc_sel = kp_raw[frame[:, None], safe][..., 2] * has[..., None]
-        p3d = _ls_persons(cgroup, und_sel, sc_sel, thr_kp)
+            for (f, rest), k, b in zip(left_groups, left_of, score_round(left_groups)):
+                persons.append((int(frames[f]), (int(ukey[k] % M), 1), b))
+    return [p for p in persons if (p[2] >= 0).sum() >= 2]                   # step2:697-698
+
+
+def associate_batch(cgroup, kp_raw, dim, cid=None, bbox_id=None, thr_kp=THR_KP, alpha_id=0.2, alpha_svt=0.5,
+                    lambda_svt=50.0, timing=None):
+    """Cross-view association + reconstruction of F keyframes at once — what
+    MultiEstimator.predict_data (step2_crossviewmatching.py:502-713) does per keyframe.
+
+      kp_raw (F, M, J, 3)  raw pixels + score of every detection, grouped by camera (padding beyond dim[:, C]);
+                           numpy, or a float64 CUDA tensor (then nothing of size F*M*J crosses the bus)
+      dim    (F, C+1)      cumulative detection counts per camera (dimGroup)
+      cid    (F, M) int    identity label per detection or -1 (None: no identity term)
+      bbox_id (F, M) int   tracklet id reported back per person and camera (None: the detection index)
+
+    Everything of size F runs on the device, all keyframes per launch: undistortion of the detections, ray
+    affinity, association weights, SVT matching, cluster labels, member tables of the persons, least-squares
+    triangulation.  The host sees the (F, M) labels, the (P, C) member tables and the result.  Keyframes in
+    which a cluster holds two detections of one camera (rare) are resolved on the host by scoring ALL
+    their candidate combinations in one batch (``_resolve_duplicate_frames``).
+
+    Returns {'label' (F,M) person column per detection or -1, 'frame' (P,), 'members' (P,C) detection index
+    per camera or -1, 'p3d' (P,J,3), 'bcomb' (P,C)}; persons are ordered by frame, then like the reference
+    (ascending cluster column; a cluster's leftover combination follows its best one)."""
+    import time as _time
+    t_last = [_time.perf_counter()]
+
+    def lap(name):
+        if timing is not None:
+            torch.cuda.synchronize()
+            now = _time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
+
+    device = cgroup._dev()
+    lib = _lib.require_gpu()
+    rig = cgroup._rig(device)
+    dev = "cuda:%d" % device
+    C = len(cgroup.cameras)
+    if _is_torch(kp_raw):
+        d_raw = kp_raw.to(device=dev, dtype=torch.float64).contiguous()
     else:
-        p3d = np.zeros((0, J, 3))
-    src = mem if bbox_id is None else np.where(has, np.asarray(bbox_id)[frame[:, None], safe], -1)
+        d_raw = torch.from_numpy(np.ascontiguousarray(kp_raw, dtype=np.float64)).to(dev)
+    F, M, J, _ = d_raw.shape
+    dim = np.ascontiguousarray(dim.cpu().numpy() if _is_torch(dim) else dim, dtype=np.int32)
+    assert dim.shape == (F, C + 1)
+    d_dim = torch.from_numpy(dim).to(dev)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = _stream(device)
+    lap("upload")
+    d_und = torch.empty_like(d_raw)
+    _lib.check(lib.m3d_undistort_detections(rig.handle, vp(d_raw), vp(d_dim), F, M, J, vp(d_und), st),
+               "m3d_undistort_detections")
+    aff = geometry_affinity_batch(cgroup, torch.nan_to_num(d_und), d_dim, thr_kp)
+    ids = np.full((F, M), -1, dtype=np.int32) if cid is None else \
+        np.ascontiguousarray(cid.cpu().numpy() if _is_torch(cid) else cid, dtype=np.int32)
+    d_cid = torch.from_numpy(ids).to(dev)
+    W = torch.empty_like(aff)
+    _lib.check(lib.m3d_association_weights(_ptr(aff), vp(d_cid), vp(d_dim), F, M, C, float(alpha_id), _ptr(W),
+                                           int(device), st), "m3d_association_weights")
+    del aff
+    lap("undistort+affinity+weights")
+    match = match_svt_batch(W, d_dim, C, alpha=alpha_svt, _lambda=lambda_svt, device=device)
+    del W
+    lap("svt")
+    d_label = torch.empty((F, M), dtype=torch.int32, device=dev)
+    _lib.check(lib.m3d_match_clusters(vp(match), vp(d_dim), F, M, C, vp(d_label), int(device), st),
+               "m3d_match_clusters")
+    del match
+    # persons as member tables, (frame, column) order: count, prefix sums, write
+    d_count = torch.empty((F,), dtype=torch.int32, device=dev)
+    d_dup = torch.empty((F,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.m3d_cluster_members(vp(d_label), vp(d_dim), F, M, C, None, vp(d_count), vp(d_dup), None, None,
+                                       None, int(device), st), "m3d_cluster_members")
+    csum = torch.cumsum(d_count, 0, dtype=torch.int64)
+    P0 = int(csum[-1].item()) if F else 0
+    d_off = (csum - d_count).contiguous()
+    d_frame = torch.empty((P0,), dtype=torch.int32, device=dev)
+    d_col = torch.empty((P0,), dtype=torch.int32, device=dev)
+    d_mem = torch.empty((P0, C), dtype=torch.int32, device=dev)
+    if P0:
+        _lib.check(lib.m3d_cluster_members(vp(d_label), vp(d_dim), F, M, C, vp(d_off), vp(d_count), vp(d_dup),
+                                           vp(d_frame), vp(d_col), vp(d_mem), int(device), st), "m3d_cluster_members")
+    label = d_label.cpu().numpy()
+    dup_frames = torch.nonzero(d_dup).reshape(-1)
+    lap("clusters")
+    if dup_frames.numel():
+        # the rare frames with duplicate detections: host bookkeeping on their rows only, merged by (frame, column)
+        fr_h = dup_frames.cpu().numpy()
+        lab_s = label[fr_h]
+        extra = _resolve_duplicate_frames(cgroup, fr_h, lab_s, _cam_of(dim[fr_h], M), d_raw[dup_frames].cpu().numpy(),
+                                          d_und[dup_frames][..., :2].cpu().numpy(), thr_kp)
+        frame = np.concatenate([d_frame.cpu().numpy().astype(np.int64), np.array([p[0] for p in extra], dtype=np.int64)])
+        col = np.concatenate([d_col.cpu().numpy().astype(np.int64) * 2,
+                              np.array([2 * p[1][0] + p[1][1] for p in extra], dtype=np.int64)])
+        mem = np.concatenate([d_mem.cpu().numpy().astype(np.int64),
+                              np.array([p[2] for p in extra], dtype=np.int64).reshape(-1, C)])
+        order = np.lexsort((col, frame))
+        frame, mem = frame[order], mem[order]
+        d_frame = torch.from_numpy(frame.astype(np.int32)).to(dev)
+        d_mem = torch.from_numpy(np.ascontiguousarray(mem, dtype=np.int32)).to(dev)
+        lap("duplicates")
+    else:
+        frame = d_frame.cpu().numpy().astype(np.int64)
+        mem = d_mem.cpu().numpy().astype(np.int64)
+    P = frame.shape[0]
+    d_p3d = torch.empty((P, J, 3), dtype=torch.float64, device=dev)
+    if P:
+        _lib.check(lib.m3d_triangulate_ls_members(rig.handle, vp(d_und), vp(d_frame), vp(d_mem), P, M, J,
+                                                  float(thr_kp), vp(d_p3d), st), "m3d_triangulate_ls_members")
+    p3d = d_p3d.cpu().numpy()
+    has = mem >= 0
+    if bbox_id is None:
+        src = mem
+    else:
+        bb = np.asarray(bbox_id.cpu().numpy() if _is_torch(bbox_id) else bbox_id)
+        src = np.where(has, bb[frame[:, None], np.where(has, mem, 0)], -1)
+    lap("triangulate+download")
     return {"label": label, "frame": frame, "members": mem, "p3d": p3d, "bcomb": np.where(has, src, -1)}
 
 

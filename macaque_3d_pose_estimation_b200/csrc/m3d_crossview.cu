@@ -461,7 +461,83 @@ k_match_clusters(const uint8_t* __restrict__ match, const int32_t* __restrict__ 
   }
 }
 
+// Persons of every keyframe as member tables (step2_crossviewmatching.py:598-607, 697-698): a person is a
+// cluster (label column) with detections from at least two cameras; members[p][c] = the detection of camera
+// c, -1 = none.  A frame with a cluster that holds TWO detections of one camera (get_best_comb territory,
+// :610-657) is flagged in `dup` and contributes no person here - the host resolves those frames.
+// One warp per frame, lane = label column (j, j + 32, ...).  Two passes of the same kernel: offsets == NULL
+// counts (count[f], dup[f]); with the exclusive prefix sums of the counts it writes frame / column / members
+// in (frame, column) order.
+__global__ void __launch_bounds__(128)
+k_cluster_members(const int32_t* __restrict__ label, const int32_t* __restrict__ dim, int F, int M, int C,
+                  const int64_t* __restrict__ offsets, int32_t* __restrict__ count, uint8_t* __restrict__ dup,
+                  int32_t* __restrict__ frame, int32_t* __restrict__ column, int32_t* __restrict__ members) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < F; f += warps) {
+    const int32_t* dg = dim + (int64_t)f * (C + 1);
+    const int32_t* lab = label + (int64_t)f * M;
+    const int nd = dg[C];
+    if (offsets && dup[f]) continue;  // warp-uniform
+    int total = 0;
+    bool any_dup = false;
+    const int64_t base = offsets ? offsets[f] : 0;
+    for (int j0 = 0; j0 < nd; j0 += 32) {
+      const int j = j0 + lane;
+      int mem[M3D_MAX_CAMS];
+#pragma unroll
+      for (int c = 0; c < M3D_MAX_CAMS; ++c) mem[c] = -1;
+      int ncam = 0;
+      bool d = false;
+      if (j < nd) {
+        int c = 0;
+        for (int i = 0; i < nd; ++i) {
+          while (c < C && i >= dg[c + 1]) ++c;  // camera of detection i (detections are grouped by camera)
+          if (lab[i] == j) {
+#pragma unroll
+            for (int k = 0; k < M3D_MAX_CAMS; ++k) {
+              if (k == c) {
+                if (mem[k] >= 0) d = true; else { mem[k] = i; ++ncam; }
+              }
+            }
+          }
+        }
+      }
+      const bool person = ncam >= 2;
+      const unsigned pb = __ballot_sync(0xffffffffu, person);
+      any_dup = any_dup || __any_sync(0xffffffffu, d);
+      if (offsets && person) {
+        const int64_t p = base + total + __popc(pb & ((1u << lane) - 1u));
+        frame[p] = f;
+        column[p] = j;
+#pragma unroll
+        for (int c = 0; c < M3D_MAX_CAMS; ++c)
+          if (c < C) members[p * C + c] = mem[c];
+      }
+      total += __popc(pb);
+    }
+    if (!offsets && lane == 0) {
+      count[f] = any_dup ? 0 : total;
+      dup[f] = any_dup ? 1 : 0;
+    }
+  }
+}
+
 extern "C" {
+
+int m3d_cluster_members(const int32_t* label, const int32_t* dim, int32_t F, int32_t M, int32_t C,
+                        const int64_t* offsets, int32_t* count, uint8_t* dup, int32_t* frame, int32_t* column,
+                        int32_t* members, int32_t device, void* stream) {
+  if (F < 0 || M < 0 || C < 0 || C > M3D_MAX_CAMS) return m3d_fail(M3D_ERR_INVALID, "m3d_cluster_members: bad size");
+  if (F == 0) return M3D_OK;
+  if (!label || !dim || !dup || (!offsets && !count) || (offsets && (!frame || !column || !members)))
+    return m3d_fail(M3D_ERR_INVALID, "m3d_cluster_members: NULL buffer");
+  M3dDeviceGuard guard(device);
+  const int blocks = (F + 3) / 4;
+  k_cluster_members<<<blocks, 128, 0, (cudaStream_t)stream>>>(label, dim, F, M, C, offsets, count, dup, frame, column,
+                                                             members);
+  return m3d_check_launch("k_cluster_members");
+}
 
 int m3d_association_weights(const double* aff, const int32_t* cid, const int32_t* dim, int32_t F, int32_t M,
                             int32_t C, double alpha_id, double* W, int32_t device, void* stream) {

@@ -299,6 +299,74 @@ k_triangulate_ls(const __grid_constant__ RigDev rig, const double* __restrict__ 
   }
 }
 
+// K7b: undistortion of every detection of F keyframes (step2_crossviewmatching.py:306-325 applied to all
+// detections of a frame, :520-530): thread = keypoint; the camera of a detection slot follows from the
+// frame's cumulative counts; padding slots give NaN.  The score is copied.
+template <bool FULL, bool PO>
+__global__ void __launch_bounds__(256)
+k_undistort_dets(const RigDev* __restrict__ rig, const double* __restrict__ kp_raw, const int32_t* __restrict__ dim,
+                 int64_t F, int M, int J, double* __restrict__ kp_und) {
+  const int C = rig->n_cams;
+  const int64_t n = F * M * J;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fm = t / J;
+    const int64_t f = fm / M;
+    const int m = (int)(fm - f * M);
+    const int32_t* dg = dim + f * (C + 1);
+    int c = 0;
+    for (int k = 1; k <= C; ++k) c += (m >= dg[k]);
+    const double u = kp_raw[3 * t], v = kp_raw[3 * t + 1];
+    double x = qnan(), y = qnan();
+    if (c < C) undistort_point<FULL, PO>(rig->cam[c], u, v, x, y);
+    kp_und[3 * t] = x;
+    kp_und[3 * t + 1] = y;
+    kp_und[3 * t + 2] = kp_raw[3 * t + 2];
+  }
+}
+
+// np.nan_to_num of one value
+__device__ __forceinline__ double nan_to_num(double v) {
+  if (v != v) return 0.0;
+  if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
+  if (v < -1.7976931348623157e308) return -1.7976931348623157e308;
+  return v;
+}
+
+// K7c: calc_3dpose (step2_crossviewmatching.py:436-461) of P persons given as member tables: thread =
+// (person, keypoint); camera c contributes the keypoint of detection members[p][c] of frame[p] when its
+// undistorted x is not NaN and its score is >= thr_kp.
+__global__ void __launch_bounds__(256)
+k_triangulate_ls_members(const RigDev* __restrict__ rig, const double* __restrict__ kp_und,
+                         const int32_t* __restrict__ frame, const int32_t* __restrict__ members, int64_t P, int M,
+                         int J, double thr_kp, double* __restrict__ p3d) {
+  const int C = rig->n_cams;
+  const int64_t n = P * J;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = t / J;
+    const int j = (int)(t - p * J);
+    const int64_t f = frame[p];
+    Gram G;
+    gram_zero(G);
+    int cnt = 0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const int m = members[p * C + c];
+      if (m < 0) continue;
+      const double* q = kp_und + 3 * ((f * M + m) * J + j);
+      const double x = q[0], y = q[1], sc = q[2];
+      if (x == x && sc >= thr_kp) {  // ~(isnan(x) | sc < thr | isnan(sc))
+        gram_add_camera(G, rig->cam[c], nan_to_num(x), nan_to_num(y));
+        ++cnt;
+      }
+    }
+    double X = qnan(), Y = qnan(), Z = qnan();
+    if (cnt >= 2) ls_solve(G, X, Y, Z);
+    p3d[3 * t] = X;
+    p3d[3 * t + 1] = Y;
+    p3d[3 * t + 2] = Z;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // fp64 FMA peak probe (the second roofline of this path)
 // ---------------------------------------------------------------------------------------
@@ -672,6 +740,31 @@ int m3d_triangulate_ls(const m3d_rig* rig, const double* xy, const uint8_t* use,
     return fail(M3D_ERR_INVALID, "m3d_triangulate_ls: NULL buffer");
   k_triangulate_ls<<<grid_for(N, 256, sms), 256, 0, st>>>(rig->dev, xy, use, N, p3d);
   return check_launch("k_triangulate_ls");
+}
+
+int m3d_undistort_detections(const m3d_rig* rig, const double* kp_raw, const int32_t* dim, int64_t N, int32_t M,
+                             int32_t J, double* kp_und, void* stream) {
+  M3D_CHECK_RIG("m3d_undistort_detections");
+  if (M < 0 || J < 0) return fail(M3D_ERR_INVALID, "m3d_undistort_detections: bad size");
+  if (N == 0 || M == 0 || J == 0) return M3D_OK;
+  if (!kp_raw || !dim || !kp_und) return fail(M3D_ERR_INVALID, "m3d_undistort_detections: NULL buffer");
+  const int grid = grid_for(N * M * J, 256, sms);
+#define CALL(F, P) k_undistort_dets<F, P><<<grid, 256, 0, st>>>(rig->dev_g, kp_raw, dim, N, M, J, kp_und)
+  M3D_DISPATCH_MODEL(rig, CALL);
+#undef CALL
+  return check_launch("k_undistort_dets");
+}
+
+int m3d_triangulate_ls_members(const m3d_rig* rig, const double* kp_und, const int32_t* frame,
+                               const int32_t* members, int64_t N, int32_t M, int32_t J, double thr_kp,
+                               double* p3d, void* stream) {
+  M3D_CHECK_RIG("m3d_triangulate_ls_members");
+  if (M < 0 || J < 0) return fail(M3D_ERR_INVALID, "m3d_triangulate_ls_members: bad size");
+  if (N == 0 || J == 0) return M3D_OK;
+  if (!kp_und || !frame || !members || !p3d) return fail(M3D_ERR_INVALID, "m3d_triangulate_ls_members: NULL buffer");
+  k_triangulate_ls_members<<<grid_for(N * J, 256, sms), 256, 0, st>>>(rig->dev_g, kp_und, frame, members, N, M, J,
+                                                                      thr_kp, p3d);
+  return check_launch("k_triangulate_ls_members");
 }
 
 // ---- host pipelines ------------------------------------------------------------------------
