@@ -38,7 +38,19 @@ struct CertDev {
   // X_b^T E X_a = 0 for camera-frame coordinates of the same world point, then
   // gam = |E[0:2,0:2]|_2 * inv_mf[a] * inv_mf[b]
   double E[CERT_MAX_PAIRS][10];
+  // float32 forms of the same tables for the pair test (m3d_ransac_cert.cuh cert_pairs): E entries rounded
+  // to nearest (their rounding is part of the test's error budget), gam / 4 and inv_mf rounded UP
+  float Ef[CERT_MAX_PAIRS][10];
+  float inv_mf_f[M3D_MAXC];
 };
+
+// smallest float >= x * (1 + 1e-6) for x >= 0 (upper bounds that survive the conversion)
+inline float cert_up_f32(double x) {
+  if (!(x > 0.0)) return 0.0f;
+  float f = (float)(x * (1.0 + 1e-6));
+  while ((double)f < x) f = std::nextafter(f, INFINITY);
+  return f;
+}
 
 M3D_HD int pair_index(int a, int b, int C) { return a * (2 * C - a - 1) / 2 + (b - a - 1); }
 
@@ -104,6 +116,7 @@ inline void build_cert(const RigDev& rig, CertDev* cert) {
     const double fmin = std::fabs(cam.fx) < std::fabs(cam.fy) ? std::fabs(cam.fx) : std::fabs(cam.fy);
     if (mu > 0.0 && std::isfinite(fmin) && fmin > 0.0) {
       cert->inv_mf[c] = (1.0 + 1e-12) / (mu * fmin);
+      cert->inv_mf_f[c] = cert_up_f32(cert->inv_mf[c]);
       cert->ok_mask |= 1 << c;
     }
   }
@@ -135,6 +148,9 @@ inline void build_cert(const RigDev& rig, CertDev* cert) {
       }
       for (int i = 0; i < 9; ++i) E[i] /= nrm;
       E[9] = norm2x2(E[0], E[1], E[3], E[4]) * (1.0 + 1e-12) * cert->inv_mf[a] * cert->inv_mf[b];
+      float* Ef = cert->Ef[pair_index(a, b, C)];
+      for (int i = 0; i < 9; ++i) Ef[i] = (float)E[i];
+      Ef[9] = cert_up_f32(0.25 * E[9]);
     }
   }
 }

@@ -137,8 +137,18 @@ M3D_HD double cert_eval(const RigDev& rig, const RV& raw, const XV& xh, uint32_t
 // position p at HIGHER positions.  rho_full > 0: also report (full_bad) whether some pair is flagged
 // at that larger budget — the budget of the FULL set, |S| = k — so that the full-set solve itself
 // can be skipped.  Straight-line per pair (no branch): a camera that cannot take part (no
-// certificate, unusable view, non-finite centre) carries an infinite half-budget, which makes the
-// right-hand side infinite; a NaN form compares false.
+// certificate, unusable view, non-finite or far-off centre) carries an infinite half-budget, which makes
+// the right-hand side infinite; a NaN form compares false.
+//
+// The per-camera part (delta_c, half budgets) is float64.  The 28 (120) pair forms run in FLOAT32 on the
+// otherwise idle FMA pipe, made conservative by an explicit error budget ("Floating
+// point"): with unit-Frobenius E and n_c = |(x_c, y_c, 1)|, every float32 sum of products below is within
+// 7 * 2^-24 * n_a n_b (the form) resp. 5 * 2^-24 * n_c (the gradient rows) of its exact value — inputs
+// rounded to nearest, one rounding per fma — so that
+//     F^ - 2e-6 n_a n_b  >  ((max(A^, B^) with + 2e-6 n / (mu f) inside) + g^ D^) D^ (1 + 2e-5)
+// implies the exact inequality F > (max(A, B) + g D) D that the proof needs; g^, 1 / (mu f), the half
+// budgets and n_c enter rounded UP.  A pair is flagged on px-level margins, the float32 slack is ~1e-5 of
+// the right-hand side: the flags are, for all practical purposes, those of the float64 evaluation.
 template <int NC>
 M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, const XY* xh, uint32_t u,
                        double rho, uint32_t* badrow, double rho_full = 0.0, bool* full_bad = nullptr) {
@@ -147,18 +157,25 @@ M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, co
   const uint32_t TOP = (uint32_t)(C - 1);
   // half budgets per camera: D = h[a] + h[b] = (rho + delta_a + delta_b) (1 + 1e-9); the slack on D
   // covers the comparison (the right-hand side grows faster than linearly in D)
-  double h[CC], hf[CC];
+  float h[CC], hf[CC], xf[CC], yf[CC], nf[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
-    h[c] = hf[c] = pos_inf();
+    h[c] = hf[c] = (float)pos_inf();
+    xf[c] = yf[c] = 0.0f;
+    nf[c] = 1.0f;
     badrow[c] = 0;
     if (c < C && ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0) {
       double pu, pv;
       distort_pinhole<false>(rig.cam[c], xh[c].x, xh[c].y, pu, pv);
       const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
-      if (e < 1e3) {  // finite centre, finite raw pixel
-        h[c] = (e + 0.5 * rho) * (1.0 + 1e-9);
-        hf[c] = (e + 0.5 * rho_full) * (1.0 + 1e-9);
+      const double x = xh[c].x, y = xh[c].y;
+      // finite centre inside |x|, |y| <= 100 (float32 range of the forms), finite raw pixel
+      if (e < 1e3 && fabs(x) <= 100.0 && fabs(y) <= 100.0) {
+        h[c] = (float)((e + 0.5 * rho) * (1.0 + 1e-6));        // rounded to nearest of a value inflated by 1e-6: >= exact
+        hf[c] = (float)((e + 0.5 * rho_full) * (1.0 + 1e-6));
+        xf[c] = (float)x;
+        yf[c] = (float)y;
+        nf[c] = (float)(sqrt_fast(fma(x, x, fma(y, y, 1.0))) * (1.0 + 1e-6));
       }
     }
   }
@@ -168,24 +185,25 @@ M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, co
 #pragma unroll
     for (int b = a + 1; b < CC; ++b) {
       if (b >= C) continue;
-      const double* E = cert.E[pair_index(a, b, C)];
-      const double ax = xh[a].x, ay = xh[a].y, qx = xh[b].x, qy = xh[b].y;
-      const double ea0 = fma(E[0], ax, fma(E[1], ay, E[2]));
-      const double ea1 = fma(E[3], ax, fma(E[4], ay, E[5]));
-      const double ea2 = fma(E[6], ax, fma(E[7], ay, E[8]));
-      const double F = fabs(fma(qx, ea0, fma(qy, ea1, ea2)));
-      const double tb0 = fma(E[0], qx, fma(E[3], qy, E[6]));
-      const double tb1 = fma(E[1], qx, fma(E[4], qy, E[7]));
-      const double A = (fabs(tb0) + fabs(tb1)) * cert.inv_mf[a];
-      const double B = (fabs(ea0) + fabs(ea1)) * cert.inv_mf[b];
-      const double M = A > B ? A : B;
-      const double g = 0.25 * E[9];
-      const double D = h[a] + h[b];
-      const bool bad = F > fma(g, D, M) * D;
+      const float* E = cert.Ef[pair_index(a, b, C)];
+      const float ax = xf[a], ay = yf[a], qx = xf[b], qy = yf[b];
+      const float ea0 = fmaf(E[0], ax, fmaf(E[1], ay, E[2]));
+      const float ea1 = fmaf(E[3], ax, fmaf(E[4], ay, E[5]));
+      const float ea2 = fmaf(E[6], ax, fmaf(E[7], ay, E[8]));
+      const float F = fabsf(fmaf(qx, ea0, fmaf(qy, ea1, ea2)));
+      const float tb0 = fmaf(E[0], qx, fmaf(E[3], qy, E[6]));
+      const float tb1 = fmaf(E[1], qx, fmaf(E[4], qy, E[7]));
+      const float A = (fabsf(tb0) + fabsf(tb1) + 2e-6f * nf[b]) * cert.inv_mf_f[a];
+      const float B = (fabsf(ea0) + fabsf(ea1) + 2e-6f * nf[a]) * cert.inv_mf_f[b];
+      const float M = A > B ? A : B;
+      const float g = E[9];  // gam / 4, rounded up
+      const float lhs = fmaf(-2e-6f * nf[a], nf[b], F);
+      const float D = h[a] + h[b];
+      const bool bad = lhs > fmaf(g, D, M) * D * 1.00002f;
       badrow[TOP - b] |= bad ? (1u << (TOP - a)) : 0u;
       if (full_bad) {
-        const double Df = hf[a] + hf[b];
-        fb = fb || (F > fma(g, Df, M) * Df);
+        const float Df = hf[a] + hf[b];
+        fb = fb || (lhs > fmaf(g, Df, M) * Df * 1.00002f);
       }
     }
   }
