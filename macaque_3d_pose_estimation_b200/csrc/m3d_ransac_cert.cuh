@@ -105,13 +105,25 @@ M3D_HD double cert_eval(const RigDev& rig, const RV& raw, const XV& xh, uint32_t
   const uint32_t TOP = (uint32_t)(C - 1);
   X = Y = Z = qnan();
   if (M3D_POPC(uc) < 2) return qnan();
+  // Branch-free over the cameras: every lane of a warp holds a different subset, so a branch per camera
+  // serialises eight partially filled blocks and keeps the compiler from interleaving them.  Instead every
+  // camera is processed by every lane and a 0 / 1 weight removes what the subset does not contain: the rows of
+  // an excluded camera are built from a finite stand-in observation and scaled by 0 (adds exactly +0), those of
+  // an included one by 1 (exact) — the sums are bit-identical to the branched form.
   Gram G;
   gram_zero(G);
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
-    if (c < C && ((uc >> (TOP - c)) & 1u)) {
+    if (c < C) {
+      const bool in = ((uc >> (TOP - c)) & 1u) != 0;
       const XY q = xh[c];
-      gram_add_camera(G, rig.cam[c], q.x, q.y);
+      const double w = in ? 1.0 : 0.0;
+      const double x = in ? q.x : 0.0, y = in ? q.y : 0.0;
+      const CamDev& cam = rig.cam[c];
+      gram_add_row(G, w * (x * cam.R[6] - cam.R[0]), w * (x * cam.R[7] - cam.R[1]), w * (x * cam.R[8] - cam.R[2]),
+                   w * (x * cam.t[2] - cam.t[0]));
+      gram_add_row(G, w * (y * cam.R[6] - cam.R[3]), w * (y * cam.R[7] - cam.R[4]), w * (y * cam.R[8] - cam.R[5]),
+                   w * (y * cam.t[2] - cam.t[1]));
     }
   }
   dlt_solve(G, X, Y, Z);
@@ -119,15 +131,14 @@ M3D_HD double cert_eval(const RigDev& rig, const RV& raw, const XV& xh, uint32_t
   int m = 0;
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
-    if (c < C && ((kept >> (TOP - c)) & 1u)) {
+    if (c < C) {
       double pu, pv;
       project_point<false, PO>(rig.cam[c], X, Y, Z, pu, pv);
       const XY q = raw[c];
       const double e = residual_norm(q.x - pu, q.y - pv);
-      if (e == e) {
-        sum += e;
-        ++m;
-      }
+      const bool use = (((kept >> (TOP - c)) & 1u) != 0) && (e == e);
+      sum += use ? e : 0.0;  // e >= 0: adding +0 leaves the sum as it is
+      m += use ? 1 : 0;
     }
   }
   return (m >= 2) ? sum / (double)m : qnan();
