@@ -496,10 +496,8 @@ k_cert_prep(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev 
     uint32_t v, u;
     cert_undistort<PO, NC>(rig, raw, undistort, xh, v, u);
     const int k = __popc(v);
-    uint32_t badrow[CC];
-    bool full_bad = false;
-    cert_pairs<NC>(rig, cert, raw, xh, u, cert_rho(T1, k), badrow, cert_rho(T1, k + 1), &full_bad);
-    // record i of this launch (the queue is the identity: every point has one)
+    // record i of this launch (the queue is the identity: every point has one).  The views are stored BEFORE
+    // the pair forms: 64 registers of float64 observations are dead while the 28 forms run.
     const unsigned int q = (unsigned int)i;
     double2* r = rec + ((size_t)(q >> 5) * F) * 32 + (q & 31u);
 #pragma unroll
@@ -509,6 +507,9 @@ k_cert_prep(const __grid_constant__ RigDev rig, const __grid_constant__ CertDev 
         r[(size_t)(C + c) * 32] = make_double2(xh[c].x, xh[c].y);
       }
     }
+    uint32_t badrow[CC];
+    bool full_bad = false;
+    cert_pairs<NC>(rig, cert, raw, xh, u, cert_rho(T1, k), badrow, cert_rho(T1, k + 1), &full_bad);
     // m0.z: bit 0 = the full set is still to be visited, bit 1 = it holds no flagged pair (solve it),
     // bit 2 = record of the v2 split (the full set's error has not been recorded anywhere)
     reinterpret_cast<uint4*>(r)[(size_t)(2 * C) * 32] =
