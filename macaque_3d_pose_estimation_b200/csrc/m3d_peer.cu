@@ -12,6 +12,17 @@
 
 static_assert(sizeof(cudaIpcMemHandle_t) == M3D_PEER_HANDLE_BYTES, "handle size of include/m3d.h");
 
+// like M3D_CUDA, and clears the runtime's last-error slot: a refused mapping must not surface later as the
+// result of an unrelated kernel launch
+#define M3D_PEER_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      cudaGetLastError();                                                                    \
+      return m3d_fail(M3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    }                                                                                        \
+  } while (0)
+
 extern "C" {
 
 int m3d_peer_alloc(int32_t device, int64_t bytes, void** dptr_out, uint8_t* handle_out) {
@@ -19,11 +30,12 @@ int m3d_peer_alloc(int32_t device, int64_t bytes, void** dptr_out, uint8_t* hand
   if (m3d_device_count() <= 0) return m3d_fail(M3D_ERR_NO_GPU, "m3d_peer_alloc: no CUDA device");
   M3dDeviceGuard guard(device);
   void* p = nullptr;
-  M3D_CUDA(cudaMalloc(&p, (size_t)bytes));
+  M3D_PEER_CUDA(cudaMalloc(&p, (size_t)bytes));
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, p);
   if (e != cudaSuccess) {
     cudaFree(p);
+    cudaGetLastError();
     return m3d_fail(M3D_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
   }
   std::memcpy(handle_out, &h, sizeof(h));
@@ -34,7 +46,7 @@ int m3d_peer_alloc(int32_t device, int64_t bytes, void** dptr_out, uint8_t* hand
 int m3d_peer_free(int32_t device, void* dptr) {
   if (!dptr) return M3D_OK;
   M3dDeviceGuard guard(device);
-  M3D_CUDA(cudaFree(dptr));
+  M3D_PEER_CUDA(cudaFree(dptr));
   return M3D_OK;
 }
 
@@ -46,7 +58,7 @@ int m3d_peer_open(int32_t device, const uint8_t* handle, void** dptr_out) {
   std::memcpy(&h, handle, sizeof(h));
   void* p = nullptr;
   // maps the exporter's allocation for `device`; peer access to the exporting GPU is enabled on demand
-  M3D_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  M3D_PEER_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   *dptr_out = p;
   return M3D_OK;
 }
@@ -54,14 +66,14 @@ int m3d_peer_open(int32_t device, const uint8_t* handle, void** dptr_out) {
 int m3d_peer_close(int32_t device, void* dptr) {
   if (!dptr) return M3D_OK;
   M3dDeviceGuard guard(device);
-  M3D_CUDA(cudaIpcCloseMemHandle(dptr));
+  M3D_PEER_CUDA(cudaIpcCloseMemHandle(dptr));
   return M3D_OK;
 }
 
 int m3d_peer_push(void* dst_window, const void* src_dev, int64_t bytes, void* stream) {
   if (bytes == 0) return M3D_OK;
   if (!dst_window || !src_dev || bytes < 0) return m3d_fail(M3D_ERR_INVALID, "m3d_peer_push: bad arguments");
-  M3D_CUDA(cudaMemcpyAsync(dst_window, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  M3D_PEER_CUDA(cudaMemcpyAsync(dst_window, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return M3D_OK;
 }
 

@@ -122,3 +122,45 @@ def test_single_process_spreads_numpy_input_over_all_gpus():
     for a, b in zip(rr, gr):
         assert np.array_equal(a, b, equal_nan=True)
     assert len(cg2._rig_cache[1]) == torch.cuda.device_count()   # one rig per GPU
+
+
+def test_peer_window_api_on_one_gpu():
+    """m3d_peer_alloc / push / free on a single GPU (the owner's side of the result window; the mapping side
+    needs a second process and is covered by the 2-GPU test above): the window is exported, copies land
+    where they are pushed, and opening one's own handle fails loudly instead of aliasing."""
+    import ctypes
+    import torch
+    from macaque_3d_pose_estimation_b200 import _lib
+    import __graft_entry__ as ge
+    ge.build_library()
+    lib = _lib.require_gpu()
+    base = ctypes.c_void_p()
+    handle = (ctypes.c_uint8 * 64)()
+    n = 100000
+    _lib.check(lib.m3d_peer_alloc(0, 8 * n, ctypes.byref(base), handle), "m3d_peer_alloc")
+    try:
+        assert base.value and any(bytes(handle))
+        src = torch.arange(n, dtype=torch.float64, device="cuda:0")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.m3d_peer_push(ctypes.c_void_p(base.value + 8 * 1000), ctypes.c_void_p(src.data_ptr()),
+                                     8 * (n - 1000), ctypes.c_void_p(st)), "m3d_peer_push")
+        from macaque_3d_pose_estimation_b200.sharding import _DeviceBytes
+        win = torch.as_tensor(_DeviceBytes(base.value, 8 * n), device="cuda:0").view(torch.float64)
+        torch.cuda.synchronize()
+        assert torch.equal(win[1000:], src[:n - 1000])
+        assert lib.m3d_peer_push(None, ctypes.c_void_p(src.data_ptr()), 8, ctypes.c_void_p(st)) != 0
+        other = ctypes.c_void_p()
+        rc = lib.m3d_peer_open(0, handle, ctypes.byref(other))             # own handle: CUDA refuses
+        if rc == 0:
+            _lib.check(lib.m3d_peer_close(0, other), "m3d_peer_close")
+        else:
+            assert "cudaIpcOpenMemHandle" in _lib.last_error()
+        # a refused mapping leaves no stale error behind: the next launch reports its own status
+        from macaque_3d_pose_estimation_b200 import synth
+        from macaque_3d_pose_estimation_b200.cameras import CameraGroup
+        cg = CameraGroup.from_dicts(synth.make_rig(8, "pinhole", seed=1))
+        p3d = cg.triangulate(torch.zeros((8, 4, 2), dtype=torch.float64, device="cuda:0"))
+        assert p3d.shape == (4, 3)
+        del win
+    finally:
+        _lib.check(lib.m3d_peer_free(0, base), "m3d_peer_free")
