@@ -604,7 +604,7 @@ def copy_ceiling(cx, nbytes=1 << 30, reps=3):
         return {"error": str(ex)[:200]}
 
 
-def e2e_run(cx, workload, xy_dev, n_e2e, ref_p3d, steps, f32):
+def e2e_run(cx, workload, xy_dev, n_e2e, ref_p3d, steps, f32, stage=False):
     """Same metric through the C-ABI host pipeline: pinned HOST buffers in, HOST buffers out, H2D +
     kernels + D2H inside every timed call, every rank streaming its own shard at once."""
     import torch
@@ -620,7 +620,8 @@ def e2e_run(cx, workload, xy_dev, n_e2e, ref_p3d, steps, f32):
     h_pick = h_xyp = None
     if workload == "ransac":
         h_pick = torch.empty((C, n_e2e), dtype=torch.uint8, pin_memory=True)
-        h_xyp = torch.empty((C, n_e2e, 2), dtype=in_dt, pin_memory=True)
+        # stage = what the 3D stage asks for (pipeline3d.reconstruct: outputs="picked"): no masked copy of the input
+        h_xyp = None if stage else torch.empty((C, n_e2e, 2), dtype=in_dt, pin_memory=True)
     sfx = "_f32" if f32 else ""
 
     def call():
@@ -643,7 +644,7 @@ def e2e_run(cx, workload, xy_dev, n_e2e, ref_p3d, steps, f32):
     if ref_p3d is not None:    # the pipeline's output equals the resident run (f64 input only)
         assert torch.equal(h_p3d.nan_to_num(), ref_p3d[:n_e2e].cpu().nan_to_num()), "e2e result differs"
     isz = 4 if f32 else 8
-    d2h = n_e2e * 32 + (n_e2e * C * (1 + 2 * isz) if workload == "ransac" else 0)
+    d2h = n_e2e * 32 + (n_e2e * C * (1 + (0 if stage else 2 * isz)) if workload == "ransac" else 0)
     return {"value": cx.world * n_e2e / dt, "unit": "joint-instances/s", "h2d_bytes_per_step": n_e2e * C * 2 * isz,
             "d2h_bytes_per_step": d2h, "joint_instances_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
             "input_dtype": "f32 (widened on the device)" if f32 else "f64",
@@ -804,6 +805,12 @@ def measure(cx, args, workload):
             out["e2e"] = e2e_run(cx, workload, xy_flat, n_e2e, p3d, args.steps, f32=False)
             out["e2e"]["host_numa_node"] = cx.numa
             out["e2e_f32"] = e2e_run(cx, workload, xy_flat, n_e2e, None, args.steps, f32=True)
+            if workload == "ransac":
+                # the call the 3D stage makes (step4:296-300 needs points_3d, picked_vals, errors)
+                out["e2e_stage"] = e2e_run(cx, workload, xy_flat, n_e2e, p3d, args.steps, f32=False, stage=True)
+                out["e2e_stage"]["what"] = ("m3d_triangulate_ransac_host without the points_2d output (NULL): what "
+                                            "pipeline3d.reconstruct / CameraGroup.triangulate_ransac(outputs='picked') "
+                                            "move; points_2d is the input masked by picked_vals")
             del xy_flat
         except Exception as ex:  # pragma: no cover
             out["e2e"] = {"value": None, "unit": "joint-instances/s", "error": str(ex)[:300]}
@@ -880,7 +887,7 @@ def run_gpu(args):
         "config": head["config"], "roofline": head["roofline"], "cpu_baseline": head.get("cpu_baseline"),
         "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks,
     }
-    for k in ("e2e_f32", "collective", "fast_undistort"):
+    for k in ("e2e_f32", "e2e_stage", "collective", "fast_undistort"):
         if k in head:
             line[k] = head[k]
     line.update(head["extra"])
@@ -891,7 +898,7 @@ def run_gpu(args):
         key = "cfg2" if other == "dlt" else "cfg3"
         sec = {k: second[k] for k in ("value", "ms_per_step", "gpu_launches", "config", "roofline", "e2e") if k in second}
         sec["unit"] = "joint-instances/s"
-        for k in ("e2e_f32", "collective", "cpu_baseline", "fast_undistort"):
+        for k in ("e2e_f32", "e2e_stage", "collective", "cpu_baseline", "fast_undistort"):
             if k in second:
                 sec[k] = second[k]
         sec.update(second["extra"])

@@ -241,54 +241,61 @@ class CameraGroup:
         return res if like_torch else tuple(t.cpu().numpy() for t in res)
 
     def triangulate_ransac(self, points, undistort=True, min_cams=2, progress=False,
-                           return_stats=False):
+                           return_stats=False, outputs="all"):
         """Given an CxNx2 array, this returns (points_3d (N,3), picked_vals (C,N,1) bool,
         points_2d (C,N,2), errors (N,)) (cameras.py:726-743).  With return_stats also
-        (subset_index (N,) int32, n_evaluated (N,) int32)."""
-        self._assert_cams(points)
-        n_cams, n_points, _ = points.shape
-        return self._ransac(points, undistort, min_cams, 0.5, 200.0, return_stats)
+        (subset_index (N,) int32, n_evaluated (N,) int32).
 
-    def _ransac(self, points, undistort, min_cams, threshold, init_best, return_stats):
+        ``outputs`` (not in the reference): "all" = the reference's four arrays; "picked" = points_2d is
+        not produced (None in its place) — it is the input masked by ``picked_vals``, 2/3 of the bytes
+        a host caller gets back, and step 4 only looks at its NaN pattern (step4_aniposefiltering.py:
+        299-300); "points_3d" = only points_3d and errors (step4:237)."""
+        self._assert_cams(points)
+        assert outputs in ("all", "picked", "points_3d"), "outputs must be 'all', 'picked' or 'points_3d'"
+        return self._ransac(points, undistort, min_cams, 0.5, 200.0, return_stats, outputs)
+
+    def _ransac(self, points, undistort, min_cams, threshold, init_best, return_stats, outputs="all"):
         C = len(self.cameras)
         n = points.shape[1]
         device, like_torch = self._device_of(points)
         rig = self._rig(device)
+        want_pick = outputs in ("all", "picked")
+        want_xyp = outputs == "all"
         if not like_torch:
             src = np.ascontiguousarray(points, dtype=np.float64)
             p3d = np.empty((n, 3))
-            picked = np.empty((C, n, 1), dtype=np.uint8)
-            xyp = np.empty((C, n, 2))
+            picked = np.empty((C, n, 1), dtype=np.uint8) if want_pick else None
+            xyp = np.empty((C, n, 2)) if want_xyp else None
             err = np.empty(n)
-            sub = np.empty(n, dtype=np.int32)
-            nev = np.empty(n, dtype=np.int32)
+            sub = np.empty(n, dtype=np.int32) if return_stats else None
+            nev = np.empty(n, dtype=np.int32) if return_stats else None
+            opt = lambda a: None if a is None else _np_ptr(a)
             devs = self._host_devices(n)
             if devs:
                 self._host_spans(devs, n, lambda r, a, cnt: _lib.check(r._lib.m3d_triangulate_ransac_host_span(
                     r.handle, _np_ptr(src), n, a, cnt, int(bool(undistort)), int(min_cams), float(threshold),
-                    float(init_best), _np_ptr(p3d), _np_ptr(picked), _np_ptr(xyp), _np_ptr(err), _np_ptr(sub),
-                    _np_ptr(nev)), "m3d_triangulate_ransac_host_span"))
-                res = (p3d, picked.view(np.bool_), xyp, err)
-                return res + (sub, nev) if return_stats else res
-            _lib.check(rig._lib.m3d_triangulate_ransac_host(
-                rig.handle, _np_ptr(src), n, int(bool(undistort)), int(min_cams), float(threshold),
-                float(init_best), _np_ptr(p3d), _np_ptr(picked), _np_ptr(xyp), _np_ptr(err),
-                _np_ptr(sub), _np_ptr(nev)), "m3d_triangulate_ransac_host")
-            res = (p3d, picked.view(np.bool_), xyp, err)
+                    float(init_best), _np_ptr(p3d), opt(picked), opt(xyp), _np_ptr(err), opt(sub),
+                    opt(nev)), "m3d_triangulate_ransac_host_span"))
+            else:
+                _lib.check(rig._lib.m3d_triangulate_ransac_host(
+                    rig.handle, _np_ptr(src), n, int(bool(undistort)), int(min_cams), float(threshold),
+                    float(init_best), _np_ptr(p3d), opt(picked), opt(xyp), _np_ptr(err),
+                    opt(sub), opt(nev)), "m3d_triangulate_ransac_host")
+            res = (p3d, picked.view(np.bool_) if want_pick else None, xyp, err)
             return res + (sub, nev) if return_stats else res
         src = _to_dev(points, device)
         dev = src.device
         p3d = torch.empty((n, 3), dtype=torch.float64, device=dev)
-        picked = torch.empty((C, n, 1), dtype=torch.uint8, device=dev)
-        xyp = torch.empty((C, n, 2), dtype=torch.float64, device=dev)
+        picked = torch.empty((C, n, 1), dtype=torch.uint8, device=dev) if want_pick else None
+        xyp = torch.empty((C, n, 2), dtype=torch.float64, device=dev) if want_xyp else None
         err = torch.empty((n,), dtype=torch.float64, device=dev)
-        sub = torch.empty((n,), dtype=torch.int32, device=dev)
-        nev = torch.empty((n,), dtype=torch.int32, device=dev)
+        sub = torch.empty((n,), dtype=torch.int32, device=dev) if return_stats else None
+        nev = torch.empty((n,), dtype=torch.int32, device=dev) if return_stats else None
         _lib.check(rig._lib.m3d_triangulate_ransac(
             rig.handle, _ptr(src), n, int(bool(undistort)), int(min_cams), float(threshold),
             float(init_best), _ptr(p3d), _ptr(picked), _ptr(xyp), _ptr(err), _ptr(sub), _ptr(nev),
             _stream(device)), "m3d_triangulate_ransac")
-        res = (p3d, picked.view(torch.bool), xyp, err)
+        res = (p3d, picked.view(torch.bool) if want_pick else None, xyp, err)
         return res + (sub, nev) if return_stats else res
 
     def reprojection_error(self, p3ds, p2ds, mean=False):

@@ -70,7 +70,7 @@ def _reconstruct_optim(cgroup, kp2d_f, config, ransac, joint_len_median, bodypar
         scores = kp2d_f[ia, :, :, :, 2]
         flat = pts.reshape(n_cam, n_frame * n_kp, 2)
         if ransac:
-            init = cgroup.triangulate_ransac(flat)[0]                            # step4:236-237
+            init = cgroup.triangulate_ransac(flat, outputs="points_3d")[0]        # step4:236-237
         else:
             init = cgroup.triangulate(flat)
         init = init.reshape(n_frame, n_kp, 3)
@@ -124,9 +124,11 @@ def reconstruct(cgroup, kp2d_f, score_threshold=0.5, ransac=False, optim=False, 
     # (A, C, F, J, 2) -> (C, A*F*J, 2): one launch for every animal
     pts = np.ascontiguousarray(all_points_raw.transpose(1, 0, 2, 3, 4)).reshape(n_cam, -1, 2)
     if ransac:
-        p3d, picked, p2ds, errors = cgroup.triangulate_ransac(pts, min_cams=min_cams)   # step4:296-297
-        picked_shaped = p2ds.reshape(n_cam, n_animal, n_frame, n_kp, 2)
-        good = ~np.isnan(picked_shaped[..., 0])                           # step4:299-300
+        # step4:296-300 reads points_2d only for its NaN pattern, which IS picked_vals (a picked camera has a
+        # finite raw x, cameras.py:658-659; everything else is NaN, :720): the masked copy of the input stays
+        # on the device and 128 of the 168 result bytes per joint-instance never cross PCIe
+        p3d, picked, _, errors = cgroup.triangulate_ransac(pts, min_cams=min_cams, outputs="picked")
+        good = np.asarray(picked).reshape(n_cam, n_animal, n_frame, n_kp).astype(bool)
         num_cams = picked.sum(axis=0).sum(axis=1).reshape(n_animal, n_frame, n_kp).astype('float')
     else:
         p3d, errors = cgroup.triangulate_with_error(pts)                  # step4:306-307 fused

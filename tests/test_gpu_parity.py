@@ -506,3 +506,26 @@ def test_gpu_ransac_min_cams_range(mc):
     o2 = og.triangulate_ransac(cams, p2, min_cams=mc, threshold=1.5, return_stats=True)
     h2 = cg.triangulate_possible(p2[:, :, None, :], min_cams=mc, threshold=1.5, return_stats=True)
     assert np.array_equal(o2[1], h2[1]) and np.array_equal(o2[4], h2[4]) and np.array_equal(o2[5], h2[5])
+
+
+def test_gpu_ransac_output_selection():
+    """triangulate_ransac(outputs=...): skipping points_2d (and picked_vals) changes nothing in what is returned,
+    for numpy (host pipeline) and torch (device-resident) callers; points_2d is picked_vals applied to the input
+    (what step4_aniposefiltering.py:299-300 relies on)."""
+    import torch
+    dicts = synth.make_rig(8, "pinhole", seed=77)
+    cams = fixtures.cams_from_dicts(dicts)
+    cg = CameraGroup.from_dicts(dicts)
+    X = synth.make_tracks(60, 2, seed=77).reshape(-1, 3)
+    p2 = synth.corrupt(og.project(cams, X), seed=77, p_outlier=0.2, p_missing=0.1)
+    full = cg.triangulate_ransac(p2, min_cams=3)
+    assert np.array_equal(~np.isnan(full[2][..., 0]), full[1][..., 0])          # NaN pattern of points_2d == picked
+    assert np.array_equal(np.where(full[1], p2, np.nan), full[2], equal_nan=True)
+    for src in (p2, torch.from_numpy(p2).cuda()):
+        a = cg.triangulate_ransac(src, min_cams=3, outputs="picked")
+        b = cg.triangulate_ransac(src, min_cams=3, outputs="points_3d", return_stats=True)
+        host = lambda t: t if isinstance(t, np.ndarray) else t.cpu().numpy()
+        assert a[2] is None and b[1] is None and b[2] is None and len(b) == 6
+        assert np.array_equal(host(a[0]), full[0], equal_nan=True) and np.array_equal(host(a[1]), full[1])
+        assert np.array_equal(host(a[3]), full[3]) and np.array_equal(host(b[0]), full[0], equal_nan=True)
+        assert np.array_equal(host(b[3]), full[3])
