@@ -140,11 +140,65 @@ def case_predict(s2, cv2, name, n_frames, seed, dup=0.08, drop=0.12, noise=0.4):
     print(name, "persons", len(pf), "reference %.1f s" % t_all)
 
 
+def case_step3(cv2, name, n_frames, seed):
+    """step3_crossframematching.py calc_3dpose (:254-272, score gate 0.3), calc_3dtrace (:274-302) and
+    calc_dist_pose (:304-311) executed on two synthetic tracklets in the reference's own containers:
+    T[i_cam][i_frame] = list of 2D tracks (entry[0] = bbox id, entry[5] = (J,3) keypoints), trk[i_frame][i_cam] =
+    the bbox id the tracklet uses there (-1 = none)."""
+    from src.pipeline import step3_crossframematching as s3
+    C, A, J = 8, 2, 17
+    dicts = synth.make_rig(C, "omnidir", seed=seed)
+    rng = np.random.default_rng(seed)
+    camparam = {"camera_id": [d["name"] for d in dicts], "K": [], "xi": [], "D": [], "rvecs": [], "tvecs": [], "pmat": []}
+    for d in dicts:
+        R, _ = cv2.Rodrigues(np.array(d["rotation"], dtype=np.float64))
+        t = np.array(d["translation"], dtype=np.float64).reshape(3, 1)
+        camparam["K"].append(np.array(d["K"], dtype=np.float64))
+        camparam["xi"].append(np.array(d["xi"], dtype=np.float64).reshape(1, 1))
+        camparam["D"].append(np.array(d["D"], dtype=np.float64).reshape(1, 4))
+        camparam["rvecs"].append(np.array(d["rotation"], dtype=np.float64).reshape(3, 1))
+        camparam["tvecs"].append(t)
+        camparam["pmat"].append(np.hstack([R, t]))
+    X = synth.make_tracks(n_frames, A, seed=seed) * np.array([0.6, 0.6, 0.5])
+    X[:, 1] = X[:, 0] + rng.normal(0, 60.0, size=(1, 1, 3)) + rng.normal(0, 8.0, size=X[:, 0].shape)   # a nearby second animal
+    kp = np.full((A, n_frames, C, J, 3), np.nan)
+    trk = -np.ones((A, n_frames, C), dtype=np.int64)
+    T = [[[] for _ in range(n_frames)] for _ in range(C)]
+    for f in range(n_frames):
+        for c in range(C):
+            for a in range(A):
+                if rng.random() < 0.25:
+                    continue                                   # this camera has no track of the animal in this frame
+                raw = cm.project_omnidir(X[f, a], np.ravel(camparam["rvecs"][c]), np.ravel(camparam["tvecs"][c]),
+                                         camparam["K"][c], camparam["xi"][c], np.ravel(camparam["D"][c]))
+                raw = raw + rng.normal(0, 0.5, size=(J, 2))
+                sc = rng.uniform(0.2, 1.0, size=J)              # some keypoints under the 0.3 gate
+                k3 = np.concatenate([raw, sc[:, None]], axis=1)
+                if rng.random() < 0.05:
+                    k3[rng.integers(J), :2] = np.nan            # a missing keypoint
+                bid = 10 * f + a
+                T[c][f].append([bid, 0, 0, 0, 0, k3.tolist()])
+                kp[a, f, c] = k3
+                trk[a, f, c] = bid
+    frames = np.arange(2, n_frames - 1)
+    traces = [s3.calc_3dtrace(trk[a], T, frames, camparam, "", J) for a in range(A)]
+    rmse = s3.calc_dist_pose(traces[0], traces[1])
+    poses = np.stack([s3.calc_3dpose(np.nan_to_num(kp[0, f], nan=np.nan), "", camparam) for f in range(4)])
+    arrs = rig_arrays(dicts)
+    arrs.update(kp=kp, trk=trk, frames=frames, trace0=traces[0], trace1=traces[1], rmse=np.array(rmse), poses=poses)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "rmse %.3f" % rmse, "finite trace rows", int(np.isfinite(traces[0][:, 0]).sum()))
+
+
 def main():
     s2, cv2 = import_reference_step2()
     os.makedirs(OUT, exist_ok=True)
+    if "step3" in sys.argv[1:]:
+        case_step3(cv2, "step3_traces", 24, 821)
+        return
     case_predict(s2, cv2, "predict_data_dups", 16, 811, dup=0.08, drop=0.12, noise=0.4)
     case_predict(s2, cv2, "predict_data_clean", 10, 812, dup=0.0, drop=0.0, noise=0.15)
+    case_step3(cv2, "step3_traces", 24, 821)
 
 
 if __name__ == "__main__":

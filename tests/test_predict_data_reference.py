@@ -56,3 +56,51 @@ def test_gpu_associate_batch_equals_executed_predict_data(name):
         sel = np.nonzero(res["frame"] == f)[0]
         _check_frame(g, f, [res["members"][k] for k in sel], [res["p3d"][k] for k in sel],
                      [res["bcomb"][k] for k in sel], 1e-6)
+
+
+def _step3_containers(g):
+    """The reference's containers rebuilt from the golden arrays: T[i_cam][i_frame] = list of tracks (entry[0] =
+    bbox id, entry[5] = (J,3) keypoints), trk[a][i_frame][i_cam] = bbox id or -1."""
+    kp, trk = g["kp"], g["trk"]
+    A, F, C, J, _ = kp.shape
+    T = [[[] for _ in range(F)] for _ in range(C)]
+    for f in range(F):
+        for c in range(C):
+            for a in range(A):
+                if trk[a, f, c] >= 0:
+                    T[c][f].append([int(trk[a, f, c]), 0, 0, 0, 0, kp[a, f, c].tolist()])
+    return T, trk
+
+
+@pytest.mark.gpu
+def test_gpu_step3_traces_equal_executed_reference():
+    """step3_crossframematching.py calc_3dpose (:254-272), calc_3dtrace (:274-302), calc_dist_pose (:304-311),
+    executed by oracle/make_golden_step2.py (same cv2.omnidir stand-in), against the batched call-site shims."""
+    from macaque_3d_pose_estimation_b200 import crossview as cv
+    from oracle import camera_math as cm
+    g, cams = _load("step3_traces")
+    C = g["rig_model"].shape[0]
+    camparam = {"camera_id": [str(x) for x in g["rig_names"]],
+                "K": [g["rig_K"][i] for i in range(C)], "xi": [np.array([[g["rig_xi"][i]]]) for i in range(C)],
+                "D": [g["rig_dist"][i, :4].reshape(1, 4) for i in range(C)],
+                "rvecs": [g["rig_rvec"][i].reshape(3, 1) for i in range(C)],
+                "tvecs": [g["rig_tvec"][i].reshape(3, 1) for i in range(C)],
+                "pmat": [np.hstack([cm.rodrigues(g["rig_rvec"][i]), g["rig_tvec"][i].reshape(3, 1)]) for i in range(C)]}
+    T, trk = _step3_containers(g)
+    J = g["kp"].shape[3]
+    traces = []
+    for a in range(2):
+        tr = cv.calc_3dtrace_tracklet(trk[a], T, g["frames"], camparam, "", J)
+        ref = g["trace%d" % a]
+        assert np.array_equal(np.isnan(tr), np.isnan(ref))
+        assert np.nanmax(np.abs(tr - ref)) <= 1e-6
+        traces.append(tr)
+    assert abs(cv.trace_distance(traces[0], traces[1]) - float(g["rmse"])) <= 1e-6
+    poses = cv.calc_3dpose_batch(g["kp"][0, :4], camparam, thr_kp=0.3)
+    assert np.array_equal(np.isnan(poses), np.isnan(g["poses"]))
+    assert np.nanmax(np.abs(poses - g["poses"])) <= 1e-6
+    p = cv.calc_p3d(T, trk[0], 3, camparam, n_kp=J)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        assert np.allclose(p, np.nanmean(g["poses"][3], axis=0), rtol=0, atol=1e-6)
