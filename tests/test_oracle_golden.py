@@ -110,6 +110,29 @@ def test_oracle_omnidir_roundtrip():
         assert np.abs(und - Xc[:, :2] / Xc[:, 2:3]).max() < 1e-9
 
 
+def test_oracle_omnidir_at_xi_zero_equals_installed_opencv():
+    """A partial pin of the Mei restatement against EXECUTED OpenCV: at xi = 0 (and zero skew) the unified model is
+    the pinhole model with (k1, k2, p1, p2) — projectPoints must equal cv2.projectPoints, and the 20-iteration
+    undistortion must agree with cv2.undistortPointsIter run to convergence.  The xi-dependent sphere lift is what
+    remains unpinned."""
+    import cv2
+    rng = np.random.default_rng(31)
+    for trial in range(4):
+        K = np.array([[900.0 + 40 * trial, 0.0, 1010.0], [0.0, 880.0 + 30 * trial, 760.0], [0.0, 0.0, 1.0]])
+        D = np.array([-0.12 + 0.05 * trial, 0.03, 0.001 * trial, -0.0015])
+        rvec = rng.normal(0, 0.4, 3)
+        tvec = np.array([30.0, -50.0, 2500.0]) + rng.normal(0, 40, 3)
+        X = rng.uniform([-600, -500, -300], [600, 500, 300], size=(200, 3))
+        ref, _ = cv2.projectPoints(X.reshape(-1, 1, 3), rvec, tvec, K, D)
+        got = cm.project_omnidir(X, rvec, tvec, K, 0.0, D)
+        assert np.abs(got - ref.reshape(-1, 2)).max() < 1e-9
+        uv = ref.reshape(-1, 2) + rng.normal(0, 0.5, size=(200, 2))
+        crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 200, 1e-14)
+        und_ref = cv2.undistortPointsIter(uv.reshape(-1, 1, 2), K, D, None, None, crit).reshape(-1, 2)
+        und = cm.undistort_omnidir(uv, K, D, 0.0)
+        assert np.abs(und - und_ref).max() < 1e-9
+
+
 @pytest.mark.parametrize("name", CROSS)
 def test_oracle_crossview(name):
     g, cams = fixtures.load_golden(name)
