@@ -117,9 +117,10 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
                                                              threshold, init_best, rec, counters)
       if (C == 8) {
         // 5 CTAs / SM: 96 registers without spills once the float64 views are stored before the pair forms
-        // (measured 10.9 ms per 6.8e7 points; 4 CTAs 11.0, 3 CTAs 12.4, 6 CTAs spill: 12.2)
+        // (measured 9.7 ms per 6.8e7 points; 4 CTAs 10.1, 6 CTAs spill 260 bytes: 10.7)
         if (setup_ctas == 3) { if (po) { CALLP(true, 8, 3); } else { CALLP(false, 8, 3); } }
         else if (setup_ctas == 4) { if (po) { CALLP(true, 8, 4); } else { CALLP(false, 8, 4); } }
+        else if (setup_ctas == 6) { if (po) { CALLP(true, 8, 6); } else { CALLP(false, 8, 6); } }
         else { if (po) { CALLP(true, 8, 5); } else { CALLP(false, 8, 5); } }
       } else {
         if (po) { CALLP(true, 0, 2); } else { CALLP(false, 0, 2); }

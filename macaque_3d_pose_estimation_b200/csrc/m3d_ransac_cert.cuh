@@ -29,6 +29,7 @@
 //   * the number of subsets the reference would have triangulated follows combinatorially from the
 //     stopping step (cumulative binomials), no counting loop.
 #pragma once
+#include <type_traits>
 #include "m3d_cert.h"
 #include "m3d_math.cuh"
 #include "m3d_point.cuh"
@@ -144,6 +145,17 @@ M3D_HD double cert_eval(const RigDev& rig, const RV& raw, const XV& xh, uint32_t
   return (m >= 2) ? sum / (double)m : qnan();
 }
 
+// f(integral_constant<a>, integral_constant<b>) for every camera pair a < b < CC, indices known at compile time
+template <int NC, int A, int B, class Fn>
+M3D_HD void cert_for_pairs(Fn&& f) {
+  constexpr int CC = NC > 0 ? NC : M3D_MAXC;
+  if constexpr (A < CC - 1) {
+    f(std::integral_constant<int, A>{}, std::integral_constant<int, B>{});
+    if constexpr (B + 1 < CC) cert_for_pairs<NC, A, B + 1>(f);
+    else cert_for_pairs<NC, A + 1, A + 2>(f);
+  }
+}
+
 // pair certificates at residual budget rho (m3d_cert.h): badrow[p] = certified-bad partners of bit
 // position p at HIGHER positions.  rho_full > 0: also report (full_bad) whether some pair is flagged
 // at that larger budget — the budget of the FULL set, |S| = k — so that the full-set solve itself
@@ -191,33 +203,32 @@ M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, co
     }
   }
   bool fb = false;
-#pragma unroll
-  for (int a = 0; a < CC; ++a) {
-#pragma unroll
-    for (int b = a + 1; b < CC; ++b) {
-      if (b >= C) continue;
-      const float* E = cert.Ef[pair_index(a, b, C)];
-      const float ax = xf[a], ay = yf[a], qx = xf[b], qy = yf[b];
-      const float ea0 = fmaf(E[0], ax, fmaf(E[1], ay, E[2]));
-      const float ea1 = fmaf(E[3], ax, fmaf(E[4], ay, E[5]));
-      const float ea2 = fmaf(E[6], ax, fmaf(E[7], ay, E[8]));
-      const float F = fabsf(fmaf(qx, ea0, fmaf(qy, ea1, ea2)));
-      const float tb0 = fmaf(E[0], qx, fmaf(E[3], qy, E[6]));
-      const float tb1 = fmaf(E[1], qx, fmaf(E[4], qy, E[7]));
-      const float A = (fabsf(tb0) + fabsf(tb1) + 2e-6f * nf[b]) * cert.inv_mf_f[a];
-      const float B = (fabsf(ea0) + fabsf(ea1) + 2e-6f * nf[a]) * cert.inv_mf_f[b];
-      const float M = A > B ? A : B;
-      const float g = E[9];  // gam / 4, rounded up
-      const float lhs = fmaf(-2e-6f * nf[a], nf[b], F);
-      const float D = h[a] + h[b];
-      const bool bad = lhs > fmaf(g, D, M) * D * 1.00002f;
-      badrow[TOP - b] |= bad ? (1u << (TOP - a)) : 0u;
-      if (full_bad) {
-        const float Df = hf[a] + hf[b];
-        fb = fb || (lhs > fmaf(g, Df, M) * Df * 1.00002f);
-      }
+  // every pair with COMPILE-TIME camera indices (cert_for_pairs): a nested `#pragma unroll` leaves the inner loop
+  // rolled (28 / 120 bodies), which turns the per-camera arrays above into local memory
+  cert_for_pairs<NC, 0, 1>([&](auto a_, auto b_) {
+    constexpr int a = decltype(a_)::value, b = decltype(b_)::value;
+    if (b >= C) return;
+    const float* E = cert.Ef[pair_index(a, b, C)];
+    const float ax = xf[a], ay = yf[a], qx = xf[b], qy = yf[b];
+    const float ea0 = fmaf(E[0], ax, fmaf(E[1], ay, E[2]));
+    const float ea1 = fmaf(E[3], ax, fmaf(E[4], ay, E[5]));
+    const float ea2 = fmaf(E[6], ax, fmaf(E[7], ay, E[8]));
+    const float F = fabsf(fmaf(qx, ea0, fmaf(qy, ea1, ea2)));
+    const float tb0 = fmaf(E[0], qx, fmaf(E[3], qy, E[6]));
+    const float tb1 = fmaf(E[1], qx, fmaf(E[4], qy, E[7]));
+    const float A = (fabsf(tb0) + fabsf(tb1) + 2e-6f * nf[b]) * cert.inv_mf_f[a];
+    const float B = (fabsf(ea0) + fabsf(ea1) + 2e-6f * nf[a]) * cert.inv_mf_f[b];
+    const float M = A > B ? A : B;
+    const float g = E[9];  // gam / 4, rounded up
+    const float lhs = fmaf(-2e-6f * nf[a], nf[b], F);
+    const float D = h[a] + h[b];
+    const bool bad = lhs > fmaf(g, D, M) * D * 1.00002f;
+    badrow[TOP - b] |= bad ? (1u << (TOP - a)) : 0u;
+    if (full_bad) {
+      const float Df = hf[a] + hf[b];
+      fb = fb || (lhs > fmaf(g, Df, M) * Df * 1.00002f);
     }
-  }
+  });
   if (full_bad) *full_bad = fb;
 }
 
