@@ -153,14 +153,17 @@ M3D_HD void undistort_pinhole_exact(const CamDev& c, double u, double v, double&
   yo = y;
 }
 
+// The five fixed-point iterations without the bail-out: returns a negative value when some icdist had its
+// sign bit set (icdist < 0, or -0 / negative NaN, which the literal transcription handles identically to
+// this loop) — the caller then replays the point through undistort_pinhole_exact.  Straight-line: several
+// cameras of one point can be in flight at once (cert_undistort).
 template <bool FULL>
-M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+M3D_HD int undistort_pinhole_core(const CamDev& c, double u, double v, double& xo, double& yo) {
   const double x0 = (u - c.cx) * c.ifx;
   const double y0 = (v - c.cy) * c.ify;
   double x = x0, y = y0;
   // OpenCV: "if (icdist < 0) { x = x0; y = y0; break; }".  The sign bits of the five icdist
-  // values are OR-ed on the integer pipe; a set bit (icdist < 0, or -0 / negative NaN, which
-  // the literal transcription handles identically to this loop) replays the point through it.
+  // values are OR-ed on the integer pipe.
   int neg = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -183,6 +186,58 @@ M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, d
     x = (x0 - dx) * icdist;
     y = (y0 - dy) * icdist;
   }
+  xo = x;
+  yo = y;
+  return neg;
+}
+
+// undistort_pinhole_core for G cameras of one point, written iteration by iteration ACROSS the cameras: the G
+// dependency chains (r2 -> polynomial -> reciprocal -> update, ~25 dependent float64 operations per iteration)
+// are adjacent in program order, which is what lets the hardware overlap them within one thread.  Per camera
+// the operations and their order are those of undistort_pinhole_core: identical results.
+template <bool FULL, int G>
+M3D_HD void undistort_pinhole_core_group(const CamDev* c, const double* u, const double* v, double* xo, double* yo,
+                                         int* neg) {
+  double x0[G], y0[G], x[G], y[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    x0[g] = (u[g] - c[g].cx) * c[g].ifx;
+    y0[g] = (v[g] - c[g].cy) * c[g].ify;
+    x[g] = x0[g], y[g] = y0[g];
+    neg[g] = 0;
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const double r2 = x[g] * x[g] + y[g] * y[g];
+      double icdist = rcp(1.0 + ((c[g].k[4] * r2 + c[g].k[1]) * r2 + c[g].k[0]) * r2);
+      if (FULL) icdist *= 1.0 + ((c[g].k[7] * r2 + c[g].k[6]) * r2 + c[g].k[5]) * r2;
+#if defined(__CUDA_ARCH__)
+      neg[g] |= __double2hiint(icdist);
+#else
+      neg[g] |= (icdist < 0.0) ? -1 : 0;
+#endif
+      const double x2 = x[g] + x[g], y2 = y[g] + y[g];
+      const double xy2 = x2 * y[g];
+      double dx = c[g].k[2] * xy2 + c[g].k[3] * (x2 * x[g] + r2);
+      double dy = c[g].k[3] * xy2 + c[g].k[2] * (y2 * y[g] + r2);
+      if (FULL) {
+        dx += c[g].k[8] * r2 + c[g].k[9] * r2 * r2;
+        dy += c[g].k[10] * r2 + c[g].k[11] * r2 * r2;
+      }
+      x[g] = (x0[g] - dx) * icdist;
+      y[g] = (y0[g] - dy) * icdist;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) xo[g] = x[g], yo[g] = y[g];
+}
+
+template <bool FULL>
+M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+  double x, y;
+  const int neg = undistort_pinhole_core<FULL>(c, u, v, x, y);
   if (neg < 0) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
   xo = x;
   yo = y;

@@ -8,8 +8,10 @@ namespace m3d {
 
 #if defined(__CUDA_ARCH__)
 #define M3D_POPC(x) __popc(x)
+#define M3D_CLZ(x) __clz((int)(x))
 #else
 #define M3D_POPC(x) __builtin_popcount(x)
+#define M3D_CLZ(x) __builtin_clz(x)
 #endif
 
 M3D_HD double pos_inf() {

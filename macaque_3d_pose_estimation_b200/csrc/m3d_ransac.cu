@@ -116,12 +116,13 @@ static int launch_ransac_cert(const m3d_rig* rig, const double* xy, int64_t N, i
   k_cert_prep<PO, NC, MB><<<(unsigned)blocksA, 128, 0, st>>>(rig->dev, rig->cert, xy, N, n0, n, undistort,    \
                                                              threshold, init_best, rec, counters)
       if (C == 8) {
-        // 5 CTAs / SM: 96 registers without spills once the float64 views are stored before the pair forms
-        // (measured 9.7 ms per 6.8e7 points; 4 CTAs 10.1, 6 CTAs spill 260 bytes: 10.7)
+        // 4 CTAs / SM (128 registers): the straight-line undistortion and half budgets (M3D_PREP_ILP) keep several
+        // cameras' chains in flight per thread and want the registers — measured per 6.8e7 points: 9.39 ms at
+        // 4 CTAs, 10.05 at 5 (600 bytes spilled); the branched round-2e form: 9.69 at 5 CTAs (tools/ab_prep.sh)
         if (setup_ctas == 3) { if (po) { CALLP(true, 8, 3); } else { CALLP(false, 8, 3); } }
-        else if (setup_ctas == 4) { if (po) { CALLP(true, 8, 4); } else { CALLP(false, 8, 4); } }
+        else if (setup_ctas == 5) { if (po) { CALLP(true, 8, 5); } else { CALLP(false, 8, 5); } }
         else if (setup_ctas == 6) { if (po) { CALLP(true, 8, 6); } else { CALLP(false, 8, 6); } }
-        else { if (po) { CALLP(true, 8, 5); } else { CALLP(false, 8, 5); } }
+        else { if (po) { CALLP(true, 8, 4); } else { CALLP(false, 8, 4); } }
       } else {
         if (po) { CALLP(true, 0, 2); } else { CALLP(false, 0, 2); }
       }

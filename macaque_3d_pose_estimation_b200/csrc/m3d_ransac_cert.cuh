@@ -30,6 +30,13 @@
 //     stopping step (cumulative binomials), no counting loop.
 #pragma once
 #include <type_traits>
+#ifndef M3D_PREP_ILP
+#define M3D_PREP_ILP 3  // developer switch, bits: 1 = straight-line undistortion of all cameras (cert_undistort), 2 = straight-line
+                        // half budgets (cert_pairs); 0 = per-camera branches in both (round-2e form)
+#endif
+#ifndef M3D_PREP_GROUP
+#define M3D_PREP_GROUP 4  // cameras whose undistortion iterations are interleaved in cert_undistort
+#endif
 #include "m3d_cert.h"
 #include "m3d_math.cuh"
 #include "m3d_point.cuh"
@@ -43,13 +50,14 @@ namespace m3d {
 M3D_HD int count_adm(const uint32_t* cumb, uint32_t n, int m) {
   if (m < 0) return 0;
   int ones = 0, total = 0;
-  for (int i = 15; i >= 0; --i) {
-    if ((n >> i) & 1u) {
-      const int rem = m - ones;
-      if (rem < 0) break;
-      total += (int)cumb[i * 17 + (rem < i ? rem : i)];
-      ++ones;
-    }
+  // the set bits of n from the top down (one trip per set bit: the common stop at the full set, n = 0, costs none)
+  for (uint32_t rest = n & 0xffffu; rest != 0;) {
+    const int i = 31 - M3D_CLZ(rest);
+    rest ^= 1u << i;
+    const int rem = m - ones;
+    if (rem < 0) break;
+    total += (int)cumb[i * 17 + (rem < i ? rem : i)];
+    ++ones;
   }
   if (ones <= m) total += 1;  // n itself (the loop was not cut short)
   return total - 1;           // s = 0 is not counted here
@@ -79,6 +87,45 @@ M3D_HD void cert_undistort(const RigDev& rig, const XY* raw, int undistort, XY* 
   const int C = NC > 0 ? NC : rig.n_cams;
   const uint32_t TOP = (uint32_t)(C - 1);
   v = 0, u = 0;
+#if (M3D_PREP_ILP & 1)
+  if constexpr (PO && NC > 0) {
+    // Rigs of pinhole cameras, count known at compile time: the cameras' iterations as ONE straight-line
+    // block (no validity branch, no bail-out branch between them), so that the scheduler can keep several
+    // cameras' dependency chains in flight per thread; an invalid view runs on NaN and is masked afterwards,
+    // the icdist < 0 replay of all cameras is one rare branch at the end.  Same arithmetic per camera, same
+    // results bit for bit.
+    if (undistort) {
+      double ux[CC], uy[CC];
+      int neg = 0;
+      constexpr int G = (CC % M3D_PREP_GROUP == 0) ? M3D_PREP_GROUP : 1;  // cameras in flight per thread
+#pragma unroll
+      for (int c0 = 0; c0 < CC; c0 += G) {
+        double ru[G], rv[G];
+        int ng[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) ru[g] = raw[c0 + g].x, rv[g] = raw[c0 + g].y;
+        undistort_pinhole_core_group<false, G>(&rig.cam[c0], ru, rv, &ux[c0], &uy[c0], ng);
+#pragma unroll
+        for (int g = 0; g < G; ++g) neg |= (ru[g] == ru[g]) ? ng[g] : 0;
+      }
+      if (neg < 0) {  // rare; unrolled (a run-time camera index would put ux / uy in local memory)
+#pragma unroll
+        for (int c = 0; c < CC; ++c)
+          if (raw[c].x == raw[c].x) undistort_pinhole<false>(rig.cam[c], raw[c].x, raw[c].y, ux[c], uy[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        const bool valid = raw[c].x == raw[c].x;  // raw x not NaN (cameras.py:658-659)
+        const double x = valid ? ux[c] : raw[c].x, y = valid ? uy[c] : raw[c].y;
+        v |= valid ? (1u << (TOP - c)) : 0u;
+        u |= (valid && x == x) ? (1u << (TOP - c)) : 0u;  // usable inside triangulate (cameras.py:630)
+        xh[c].x = x;
+        xh[c].y = y;
+      }
+      return;
+    }
+  }
+#endif
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
     if (c < C) {
@@ -187,18 +234,37 @@ M3D_HD void cert_pairs(const RigDev& rig, const CertDev& cert, const XY* raw, co
     xf[c] = yf[c] = 0.0f;
     nf[c] = 1.0f;
     badrow[c] = 0;
-    if (c < C && ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0) {
+    if constexpr ((M3D_PREP_ILP & 2) != 0 && NC > 0) {
+      // straight-line over the cameras (the per-camera branches of the general form below serialise the eight
+      // distortion + square-root chains): computed for every camera, kept by a select — a view that takes no
+      // part (NaN centre, no certificate) fails the comparisons and keeps the infinite half-budget
       double pu, pv;
       distort_pinhole<false>(rig.cam[c], xh[c].x, xh[c].y, pu, pv);
       const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
       const double x = xh[c].x, y = xh[c].y;
-      // finite centre inside |x|, |y| <= 100 (float32 range of the forms), finite raw pixel
-      if (e < 1e3 && fabs(x) <= 100.0 && fabs(y) <= 100.0) {
-        h[c] = (float)((e + 0.5 * rho) * (1.0 + 1e-6));        // rounded to nearest of a value inflated by 1e-6: >= exact
-        hf[c] = (float)((e + 0.5 * rho_full) * (1.0 + 1e-6));
-        xf[c] = (float)x;
-        yf[c] = (float)y;
-        nf[c] = (float)(sqrt_fast(fma(x, x, fma(y, y, 1.0))) * (1.0 + 1e-6));
+      const bool ok = ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0 && e < 1e3 && fabs(x) <= 100.0 && fabs(y) <= 100.0;
+      const float hc = (float)((e + 0.5 * rho) * (1.0 + 1e-6));
+      const float hfc = (float)((e + 0.5 * rho_full) * (1.0 + 1e-6));
+      const float nfc = (float)(sqrt_fast(fma(x, x, fma(y, y, 1.0))) * (1.0 + 1e-6));
+      h[c] = ok ? hc : h[c];
+      hf[c] = ok ? hfc : hf[c];
+      xf[c] = ok ? (float)x : 0.0f;
+      yf[c] = ok ? (float)y : 0.0f;
+      nf[c] = ok ? nfc : 1.0f;
+    } else {
+      if (c < C && ((u >> (TOP - c)) & 1u) && cert.inv_mf[c] > 0.0) {
+        double pu, pv;
+        distort_pinhole<false>(rig.cam[c], xh[c].x, xh[c].y, pu, pv);
+        const double e = residual_norm(raw[c].x - pu, raw[c].y - pv);
+        const double x = xh[c].x, y = xh[c].y;
+        // finite centre inside |x|, |y| <= 100 (float32 range of the forms), finite raw pixel
+        if (e < 1e3 && fabs(x) <= 100.0 && fabs(y) <= 100.0) {
+          h[c] = (float)((e + 0.5 * rho) * (1.0 + 1e-6));        // rounded to nearest of a value inflated by 1e-6: >= exact
+          hf[c] = (float)((e + 0.5 * rho_full) * (1.0 + 1e-6));
+          xf[c] = (float)x;
+          yf[c] = (float)y;
+          nf[c] = (float)(sqrt_fast(fma(x, x, fma(y, y, 1.0))) * (1.0 + 1e-6));
+        }
       }
     }
   }

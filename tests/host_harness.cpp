@@ -317,7 +317,10 @@ int hh_ransac_cert(const m3d_cam* cams, int C, const double* xy, int64_t N, int 
       raw[c].y = xy[2 * ((int64_t)c * N + n) + 1];
     }
     CertOut o;
-    if (po) ransac_cert_point<true, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
+    // 8-camera pinhole rigs: the compile-time-count instantiation the kernels of the headline config run
+    // (straight-line undistortion / half budgets of cert_undistort and cert_pairs)
+    if (po && C == 8) ransac_cert_point<true, 8>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
+    else if (po) ransac_cert_point<true, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
     else ransac_cert_point<false, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
     p3d[3 * n] = o.X;
     p3d[3 * n + 1] = o.Y;
