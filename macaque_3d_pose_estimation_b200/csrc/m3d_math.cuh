@@ -234,10 +234,47 @@ M3D_HD void undistort_pinhole_core_group(const CamDev* c, const double* u, const
   for (int g = 0; g < G; ++g) xo[g] = x[g], yo[g] = y[g];
 }
 
+// undistort_pinhole through undistort_pinhole_core: the replay of a flagged point in cert_undistort
 template <bool FULL>
-M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+M3D_HD void undistort_pinhole_replay(const CamDev& c, double u, double v, double& xo, double& yo) {
   double x, y;
   const int neg = undistort_pinhole_core<FULL>(c, u, v, x, y);
+  if (neg < 0) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
+  xo = x;
+  yo = y;
+}
+
+// One camera, one point (every kernel but the straight-line form of cert_undistort).
+template <bool FULL>
+M3D_HD void undistort_pinhole(const CamDev& c, double u, double v, double& xo, double& yo) {
+  const double x0 = (u - c.cx) * c.ifx;
+  const double y0 = (v - c.cy) * c.ify;
+  double x = x0, y = y0;
+  // OpenCV: "if (icdist < 0) { x = x0; y = y0; break; }".  The sign bits of the five icdist
+  // values are OR-ed on the integer pipe; a set bit (icdist < 0, or -0 / negative NaN, which
+  // the literal transcription handles identically to this loop) replays the point through it.
+  int neg = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    double icdist = rcp(1.0 + ((c.k[4] * r2 + c.k[1]) * r2 + c.k[0]) * r2);
+    if (FULL) icdist *= 1.0 + ((c.k[7] * r2 + c.k[6]) * r2 + c.k[5]) * r2;
+#if defined(__CUDA_ARCH__)
+    neg |= __double2hiint(icdist);
+#else
+    neg |= (icdist < 0.0) ? -1 : 0;
+#endif
+    const double x2 = x + x, y2 = y + y;
+    const double xy2 = x2 * y;
+    double dx = c.k[2] * xy2 + c.k[3] * (x2 * x + r2);
+    double dy = c.k[3] * xy2 + c.k[2] * (y2 * y + r2);
+    if (FULL) {
+      dx += c.k[8] * r2 + c.k[9] * r2 * r2;
+      dy += c.k[10] * r2 + c.k[11] * r2 * r2;
+    }
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
   if (neg < 0) undistort_pinhole_exact<FULL>(c, u, v, x, y);  // rare (k1 << 0 at image corners)
   xo = x;
   yo = y;

@@ -111,7 +111,7 @@ M3D_HD void cert_undistort(const RigDev& rig, const XY* raw, int undistort, XY* 
       if (neg < 0) {  // rare; unrolled (a run-time camera index would put ux / uy in local memory)
 #pragma unroll
         for (int c = 0; c < CC; ++c)
-          if (raw[c].x == raw[c].x) undistort_pinhole<false>(rig.cam[c], raw[c].x, raw[c].y, ux[c], uy[c]);
+          if (raw[c].x == raw[c].x) undistort_pinhole_replay<false>(rig.cam[c], raw[c].x, raw[c].y, ux[c], uy[c]);
       }
 #pragma unroll
       for (int c = 0; c < CC; ++c) {
