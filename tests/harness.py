@@ -120,8 +120,10 @@ def cert_tables(cams):
 
 
 def ransac_cert(cams, xy, undistort=True, min_cams=2, threshold=0.5, init_best=200.0, use_cert=True,
-                return_solved=False):
-    """The pruned subset search (csrc/m3d_ransac_cert.cuh ransac_cert_point) on the host."""
+                return_solved=False, general=False):
+    """The pruned subset search (csrc/m3d_ransac_cert.cuh ransac_cert_point) on the host.  8-camera pinhole
+    rigs run the compile-time-count instantiation of the headline kernels (straight-line undistortion and half
+    budgets); ``general=True`` forces the run-time-count form every other rig takes."""
     xy = np.ascontiguousarray(xy, dtype=np.float64)
     C, n = len(cams), xy.shape[1]
     p3d = np.empty((n, 3))
@@ -132,7 +134,7 @@ def ransac_cert(cams, xy, undistort=True, min_cams=2, threshold=0.5, init_best=2
     nev = np.empty(n, dtype=np.int32)
     solved = np.empty(n, dtype=np.int32)
     _ok(load().hh_ransac_cert(cam_structs(cams), C, _p(xy), ctypes.c_int64(n), int(undistort), int(min_cams),
-                              ctypes.c_double(threshold), ctypes.c_double(init_best), int(use_cert), _p(p3d),
+                              ctypes.c_double(threshold), ctypes.c_double(init_best), int(bool(use_cert)) | (2 if general else 0), _p(p3d),
                               _p(picked), _p(xyp), _p(err), _p(sub), _p(nev), _p(solved)))
     res = (p3d, picked.view(np.bool_), xyp, err, sub, nev)
     return res + (solved,) if return_solved else res

@@ -319,9 +319,11 @@ int hh_ransac_cert(const m3d_cam* cams, int C, const double* xy, int64_t N, int 
     CertOut o;
     // 8-camera pinhole rigs: the compile-time-count instantiation the kernels of the headline config run
     // (straight-line undistortion / half budgets of cert_undistort and cert_pairs)
-    if (po && C == 8) ransac_cert_point<true, 8>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
-    else if (po) ransac_cert_point<true, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
-    else ransac_cert_point<false, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, use_cert != 0, o);
+    // use_cert: bit 0 = prune by the pair certificates, bit 1 = force the run-time-count instantiation
+    const bool prune = (use_cert & 1) != 0, general = (use_cert & 2) != 0;
+    if (po && C == 8 && !general) ransac_cert_point<true, 8>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, prune, o);
+    else if (po) ransac_cert_point<true, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, prune, o);
+    else ransac_cert_point<false, 0>(rig, cert, &cumb.v[0][0], raw, undistort, min_cams, threshold, init_best, prune, o);
     p3d[3 * n] = o.X;
     p3d[3 * n + 1] = o.Y;
     p3d[3 * n + 2] = o.Z;

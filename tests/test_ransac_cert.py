@@ -149,6 +149,45 @@ def test_host_pruned_search_goldens(name):
     assert np.abs(got[3] - g["errors"]).max() <= 1e-7
 
 
+@pytest.mark.parametrize("case", ["bench", "barrel", "sparse"])
+@pytest.mark.parametrize("use_cert", [True, False])
+def test_host_straight_line_form_equals_general_form_bit_for_bit(case, use_cert):
+    """The compile-time-count instantiation of the headline kernels (cert_undistort / cert_pairs as straight-line
+    code over the eight cameras, invalid views run on NaN and are masked, one replay branch for icdist < 0) against
+    the run-time-count form with its per-camera branches: every output identical to the last bit."""
+    dicts = synth.make_rig(8, "pinhole", seed=31)
+    rng = np.random.default_rng(31)
+    if case == "barrel":   # k1 << 0: icdist < 0 at the image corners (cv2's bail-out, the replay branch)
+        for d in dicts:
+            d["distortions"] = [-0.9, 0.0, 0.0, 0.0, 0.0]
+    cams = fixtures.cams_from_dicts(dicts)
+    X = synth.make_tracks(60, 2, seed=31).reshape(-1, 3)
+    p2d = synth.corrupt(og.project(cams, X), seed=31, p_outlier=0.25, p_missing=0.6 if case == "sparse" else 0.12)
+    if case == "barrel":   # observations all over the image, corners included
+        n = p2d.shape[1]
+        far = rng.random((8, n)) < 0.3
+        p2d[far] = np.stack([rng.uniform(0, 2048, far.sum()), rng.uniform(0, 1536, far.sum())], axis=1)
+    p2d[2, 3, 1] = np.nan          # y missing only
+    p2d[4, 4, 0] = np.nan          # x missing only
+    p2d[:, 5] = np.nan
+    p2d[1:, 6] = np.nan
+    a = harness.ransac_cert(cams, p2d, use_cert=use_cert, return_solved=True)
+    b = harness.ransac_cert(cams, p2d, use_cert=use_cert, return_solved=True, general=True)
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and x.tobytes() == y.tobytes()
+    if case == "barrel":   # the replay branch is really taken: some icdist of the five iterations is negative
+        K = np.array(dicts[0]["matrix"])
+        x0 = (p2d[0, :, 0] - K[0, 2]) / K[0, 0]
+        y0 = (p2d[0, :, 1] - K[1, 2]) / K[1, 1]
+        x, y, neg = x0.copy(), y0.copy(), np.zeros(x0.shape, dtype=bool)
+        with np.errstate(all="ignore"):
+            for _ in range(5):
+                icd = 1.0 / (1.0 - 0.9 * (x * x + y * y))
+                neg |= icd < 0
+                x, y = x0 * icd, y0 * icd
+        assert neg.sum() >= 3
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU tier
 # ---------------------------------------------------------------------------------------------
