@@ -1,6 +1,12 @@
 #!/bin/bash
 # Developer tool (run under gpurun): A/B of the k_cert_prep variants (M3D_PREP_ILP builds under tools/_alt/,
 # CTAs per SM), then parity + stress + default bench + captures with the fastest one installed.
+# The variant libraries are built beforehand in the build container (git-ignored, they travel with the snapshot):
+#   cd macaque_3d_pose_estimation_b200/csrc && for v in 0 1 2; do
+#     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DM3D_PREP_ILP=$v \
+#          -c -o /tmp/ransac_v$v.o m3d_ransac.cu
+#     nvcc -shared -o ../../tools/_alt/libm3d_ilp$v.so /tmp/ransac_v$v.o $(ls _obj/*.o | grep -v m3d_ransac.o); done
+# (libm3d.so itself is the M3D_PREP_ILP=3 build.)  Result of the round-2 run: profiles/r02g_ab_prep.txt.
 t0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - t0 ))s] $1"; }
 L=macaque_3d_pose_estimation_b200/csrc/libm3d.so
